@@ -1,0 +1,203 @@
+"""lajolla_public_b200 -- host-side mirror of lajolla's rendering interface over the CUDA C ABI.
+
+Names follow the reference (BachiLi/lajolla_public): `parse_scene` (parsers/parse_scene.h:9),
+`render` (render.h:9), `intersect` / `occluded` (intersection.h:39-46), `eval` / `pdf_sample_bsdf` /
+`sample_bsdf` (material.h:119-163), `sample_primary` (camera.h:27-28).  Everything executes in
+libljb200.so on a B200 (include/lajolla_b200.h); this package only marshals buffers.  There is no
+CPU implementation behind it: without the built library or without a CUDA device calls raise.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from . import abi, ljs
+from .abi import LajollaError, load_library
+
+__all__ = ["Scene", "parse_scene", "render", "LajollaError", "load_library", "abi", "ljs"]
+
+RAY_DTYPE = np.dtype([("org", "<f4", 3), ("tnear", "<f4"), ("dir", "<f4", 3), ("tfar", "<f4")])
+HIT_DTYPE = np.dtype([("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("shape_id", "<i4"), ("primitive_id", "<i4")])
+VERTEX_DTYPE = np.dtype([("position", "<f4", 3), ("geometric_normal", "<f4", 3), ("frame_x", "<f4", 3),
+                         ("frame_y", "<f4", 3), ("frame_n", "<f4", 3), ("st", "<f4", 2), ("uv", "<f4", 2),
+                         ("uv_screen_size", "<f4"), ("mean_curvature", "<f4"), ("ray_radius", "<f4"),
+                         ("shape_id", "<i4"), ("primitive_id", "<i4"), ("material_id", "<i4"),
+                         ("interior_medium_id", "<i4"), ("exterior_medium_id", "<i4")])
+BSDF_QUERY_DTYPE = np.dtype([("vertex", VERTEX_DTYPE), ("dir_in", "<f4", 3), ("dir_out", "<f4", 3),
+                             ("rnd_uv", "<f4", 2), ("rnd_w", "<f4"), ("transport", "<i4")])
+BSDF_RESULT_DTYPE = np.dtype([("f", "<f4", 3), ("pdf", "<f4"), ("sampled", "<i4"), ("s_dir_out", "<f4", 3),
+                              ("s_eta", "<f4"), ("s_roughness", "<f4")])
+LIGHT_QUERY_DTYPE = np.dtype([("ref_point", "<f4", 3), ("rnd_uv", "<f4", 2), ("rnd_w", "<f4"), ("light_w", "<f4")])
+LIGHT_RESULT_DTYPE = np.dtype([("light_id", "<i4"), ("position", "<f4", 3), ("normal", "<f4", 3), ("pmf", "<f4"),
+                               ("pdf", "<f4"), ("emission", "<f4", 3)])
+
+assert RAY_DTYPE.itemsize == C.sizeof(abi.lj_ray) and HIT_DTYPE.itemsize == C.sizeof(abi.lj_hit)
+assert VERTEX_DTYPE.itemsize == C.sizeof(abi.lj_vertex)
+assert BSDF_QUERY_DTYPE.itemsize == C.sizeof(abi.lj_bsdf_query)
+assert BSDF_RESULT_DTYPE.itemsize == C.sizeof(abi.lj_bsdf_result)
+assert LIGHT_QUERY_DTYPE.itemsize == C.sizeof(abi.lj_light_query)
+assert LIGHT_RESULT_DTYPE.itemsize == C.sizeof(abi.lj_light_result)
+
+
+def _ptr(a, ctype):
+    return a.ctypes.data_as(C.POINTER(ctype))
+
+
+def make_rays(org, dir, tnear=0.0, tfar=np.inf):
+    org = np.asarray(org, dtype=np.float32).reshape(-1, 3)
+    r = np.zeros(org.shape[0], dtype=RAY_DTYPE)
+    r["org"] = org
+    r["dir"] = np.asarray(dir, dtype=np.float32).reshape(-1, 3)
+    r["tnear"] = tnear
+    r["tfar"] = tfar
+    return r
+
+
+class Scene:
+    """Device-resident scene (the reference's `Scene`, scene.h:39-88): BVH, mip chains and sampling
+    tables are built on the GPU by lj_scene_create."""
+
+    def __init__(self, desc: ljs.SceneDesc, device: int = 0):
+        self._lib = load_library()
+        abi.check(self._lib.lj_init(device))
+        cdesc, keep = ljs.to_c(desc)
+        h = C.c_void_p()
+        abi.check(self._lib.lj_scene_create(C.byref(cdesc), C.byref(h)))
+        del keep
+        self._h = h
+        self.desc = desc
+        self.width, self.height = desc.camera.width, desc.camera.height
+        self.last_stats = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.lj_scene_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- S1
+    def render(self, spp=0, sample_begin=0, sample_end=0, normalize=True, pool_paths=0, seed=0, variance=False):
+        opts = abi.lj_render_opts(spp, sample_begin, sample_end, 1 if normalize else 0, pool_paths, seed, None)
+        out = np.empty((self.height, self.width, 3), dtype=np.float32)
+        var = None
+        if variance:
+            var = np.empty((self.height, self.width, 3), dtype=np.float32)
+            opts.variance_out = _ptr(var, C.c_float)
+        stats = abi.lj_stats()
+        abi.check(self._lib.lj_render(self._h, C.byref(opts), _ptr(out, C.c_float), C.byref(stats)))
+        self.last_stats = stats
+        return (out, var) if variance else out
+
+    def render_device(self, d_out_ptr, stream_ptr=None, spp=0, sample_begin=0, sample_end=0, normalize=False, pool_paths=0, seed=0):
+        """Render into DEVICE memory (w*h*3 fp32 at d_out_ptr) on the given cudaStream_t."""
+        opts = abi.lj_render_opts(spp, sample_begin, sample_end, 1 if normalize else 0, pool_paths, seed, None)
+        stats = abi.lj_stats()
+        abi.check(self._lib.lj_render_device(self._h, C.byref(opts), C.c_void_p(d_out_ptr), C.c_void_p(stream_ptr or 0), C.byref(stats)))
+        self.last_stats = stats
+        return stats
+
+    # ---- S2
+    def intersect_hits(self, rays, want_ms=False):
+        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        hits = np.zeros(rays.shape[0], dtype=HIT_DTYPE)
+        ms = C.c_double(0)
+        abi.check(self._lib.lj_trace_closest(self._h, _ptr(rays, abi.lj_ray), rays.shape[0], _ptr(hits, abi.lj_hit), C.byref(ms)))
+        return (hits, ms.value) if want_ms else hits
+
+    def occluded(self, rays, want_ms=False):
+        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        occ = np.zeros(rays.shape[0], dtype=np.uint8)
+        ms = C.c_double(0)
+        abi.check(self._lib.lj_trace_any(self._h, _ptr(rays, abi.lj_ray), rays.shape[0], _ptr(occ, C.c_uint8), C.byref(ms)))
+        return (occ.astype(bool), ms.value) if want_ms else occ.astype(bool)
+
+    def intersect(self, rays, ray_diff=None):
+        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        out = np.zeros(rays.shape[0], dtype=VERTEX_DTYPE)
+        rd = None
+        if ray_diff is not None:
+            rd = np.ascontiguousarray(ray_diff, dtype=np.float32).reshape(-1, 2)
+        abi.check(self._lib.lj_intersect(self._h, _ptr(rays, abi.lj_ray), _ptr(rd, C.c_float) if rd is not None else None,
+                                         rays.shape[0], _ptr(out, abi.lj_vertex)))
+        return out
+
+    def bsdf(self, queries):
+        q = np.ascontiguousarray(queries, dtype=BSDF_QUERY_DTYPE)
+        out = np.zeros(q.shape[0], dtype=BSDF_RESULT_DTYPE)
+        abi.check(self._lib.lj_bsdf_batch(self._h, _ptr(q, abi.lj_bsdf_query), q.shape[0], _ptr(out, abi.lj_bsdf_result)))
+        return out
+
+    def sample_lights(self, queries):
+        q = np.ascontiguousarray(queries, dtype=LIGHT_QUERY_DTYPE)
+        out = np.zeros(q.shape[0], dtype=LIGHT_RESULT_DTYPE)
+        abi.check(self._lib.lj_light_batch(self._h, _ptr(q, abi.lj_light_query), q.shape[0], _ptr(out, abi.lj_light_result)))
+        return out
+
+    def sample_primary(self, screen_pos):
+        xy = np.ascontiguousarray(screen_pos, dtype=np.float32).reshape(-1, 2)
+        rays = np.zeros(xy.shape[0], dtype=RAY_DTYPE)
+        abi.check(self._lib.lj_camera_rays(self._h, _ptr(xy, C.c_float), xy.shape[0], _ptr(rays, abi.lj_ray)))
+        return rays
+
+    def eval_texture(self, material_id, slot, uv_footprint):
+        q = np.ascontiguousarray(uv_footprint, dtype=np.float32).reshape(-1, 3)
+        out = np.zeros((q.shape[0], 3), dtype=np.float32)
+        abi.check(self._lib.lj_texture_batch(self._h, material_id, slot, _ptr(q, C.c_float), q.shape[0], _ptr(out, C.c_float)))
+        return out
+
+    def info(self):
+        i = abi.lj_scene_info()
+        abi.check(self._lib.lj_scene_get_info(self._h, C.byref(i)))
+        return i
+
+    def light_table(self):
+        n = len(self.desc.lights)
+        pmf = np.zeros(n, dtype=np.float32)
+        cdf = np.zeros(n + 1, dtype=np.float32)
+        abi.check(self._lib.lj_scene_get_light_table(self._h, _ptr(pmf, C.c_float), _ptr(cdf, C.c_float)))
+        return pmf, cdf
+
+    def mip_level(self, image_id, level):
+        ch = self.desc.images[image_id].shape[2]
+        w, h = C.c_int32(0), C.c_int32(0)
+        abi.check(self._lib.lj_scene_get_mip_level(self._h, ch, image_id, level, C.byref(w), C.byref(h), None))
+        data = np.zeros((h.value, w.value, ch), dtype=np.float32)
+        abi.check(self._lib.lj_scene_get_mip_level(self._h, ch, image_id, level, C.byref(w), C.byref(h), _ptr(data, C.c_float)))
+        return data
+
+
+def pcg32(first_stream, n_streams, n_draws, seed=0):
+    lib = load_library()
+    u = np.zeros((n_streams, n_draws), dtype=np.uint32)
+    f = np.zeros((n_streams, n_draws), dtype=np.float32)
+    abi.check(lib.lj_pcg32_batch(first_stream, seed, n_streams, n_draws, _ptr(u, C.c_uint32), _ptr(f, C.c_float)))
+    return u, f
+
+
+LAJOLLA_CLI = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lajolla")
+
+
+def parse_scene(path, device: int = 0) -> Scene:
+    """parse_scene() of the reference (parsers/parse_scene.cpp:1602).  `.ljs` files are loaded directly;
+    Mitsuba-style XML goes through the C++ host front end (`lajolla --dump-ljs`)."""
+    path = str(path)
+    if path.endswith(".ljs"):
+        return Scene(ljs.load(path), device)
+    if not os.path.exists(LAJOLLA_CLI):
+        raise ImportError(f"{LAJOLLA_CLI} not built (make -C lajolla_public_b200)")
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        out = os.path.join(tmp, "scene.ljs")
+        subprocess.run([LAJOLLA_CLI, "--dump-ljs", out, path], check=True, stdout=subprocess.DEVNULL)
+        return Scene(ljs.load(out), device)
+
+
+def render(scene: Scene, **kw):
+    """Image3 render(const Scene&) (render.cpp:155): returns (h, w, 3) float32."""
+    return scene.render(**kw)

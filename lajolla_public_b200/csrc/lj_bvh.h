@@ -1,0 +1,146 @@
+// lj_bvh.h -- ray/primitive tests and stack traversal of the GPU-built BVH.
+// Replaces rtcIntersect1 / rtcOccluded1 (reference intersection.cpp:32,83) and the sphere user
+// geometry callbacks (shapes/sphere.inl:40-149).  Hit conventions follow Embree's as the reference
+// consumes them: p = (1-u-v) v0 + u v1 + v v2, Ng = (v1-v0)x(v2-v0)
+// unnormalised, triangle hit iff tnear <= t <= tfar, sphere hit iff tnear <= t < tfar.
+#pragma once
+#include "lj_scene_dev.h"
+
+namespace lj {
+
+constexpr int kNoHit = -1;
+
+struct Hit {
+    float t, u, v;
+    int prim;  // index into DevScene::prims (BVH leaf order), kNoHit on miss
+};
+
+// Pluecker edge-function test (the formulation of Embree's ROBUST triangle intersector) in fp32.
+// The edge functions of a shared edge are exact negations of each other in the two triangles, so
+// the inclusive sign test is watertight along shared edges.
+LJ_HD bool hit_triangle(V3 A, V3 B, V3 C, V3 o, V3 d, float tnear, float tfar, float &t, float &u, float &v) {
+    V3 v0 = A - o, v1 = B - o, v2 = C - o;
+    V3 e0 = v2 - v0, e1 = v0 - v1, e2 = v1 - v2;
+    float U = dot(cross(e0, v2 + v0), d);
+    float V = dot(cross(e1, v0 + v1), d);
+    float W = dot(cross(e2, v1 + v2), d);
+    float mn = fminf(U, fminf(V, W)), mx = fmaxf(U, fmaxf(V, W));
+    if (!(mn >= 0 || mx <= 0)) return false;
+    float UVW = U + V + W;
+    if (UVW == 0) return false;
+    V3 Ng = cross(e0, e1);
+    float den = dot(Ng, d);
+    if (den == 0) return false;
+    float tt = dot(v0, Ng) / den;
+    if (!(tt >= tnear && tt <= tfar)) return false;
+    t = tt;
+    float r = 1 / UVW;
+    u = fminf(U * r, 1.0f);
+    v = fminf(V * r, 1.0f);
+    return true;
+}
+
+// Ray/sphere, nearest root in [tnear, tfar) like sphere.inl:40-106.  fp32 needs a better
+// conditioned discriminant than b^2-4ac: it is taken from the perpendicular offset of the centre
+// (Haines et al., "Precision improvements for ray/sphere intersection").
+LJ_HD bool hit_sphere(V3 c, float r, V3 o, V3 d, float tnear, float tfar, float &t) {
+    V3 f = o - c;
+    float a = dot(d, d);
+    if (a == 0) return false;
+    float bh = -dot(f, d);
+    V3 l = f + (bh / a) * d;
+    float disc = r * r - dot(l, l);
+    if (disc < 0) return false;
+    float cc = dot(f, f) - r * r;
+    float q = bh + copysignf(sqrtf(a * disc), bh);
+    float t0 = cc / q, t1 = q / a;
+    if (q == 0) { t0 = 0; t1 = 0; }
+    if (t0 > t1) { float s = t0; t0 = t1; t1 = s; }
+    float tt = -1;
+    if (t0 >= tnear && t0 < tfar) tt = t0;
+    if (t1 >= tnear && t1 < tfar && tt < 0) tt = t1;
+    if (!(tt >= tnear && tt < tfar)) return false;
+    t = tt;
+    return true;
+}
+
+LJ_HD bool prim_is_sphere(const V4 &c) { return f2u(c.w) != 0; }
+LJ_HD int prim_shape_id(const V4 &c) { return (int)f2u(c.y); }
+LJ_HD int prim_primitive_id(const V4 &c) { return (int)f2u(c.z); }
+
+LJ_HD bool hit_prim(const DevPrim *prims, int i, V3 o, V3 d, float tnear, float tfar, float &t, float &u, float &v) {
+    V4 a = ld4(&prims[i].a);
+    V4 c = ld4(&prims[i].c);
+    if (prim_is_sphere(c)) {
+        u = 0; v = 0;
+        return hit_sphere(xyz(a), a.w, o, d, tnear, tfar, t);
+    }
+    V4 b = ld4(&prims[i].b);
+    return hit_triangle(xyz(a), mk3(a.w, b.x, b.y), mk3(b.z, b.w, c.x), o, d, tnear, tfar, t, u, v);
+}
+
+// Stack traversal of the binary BVH (DevNode2).  ANY = true stops at the first hit.
+// Edge-tie policy: a later candidate replaces the current hit only if strictly
+// nearer, so among exactly equal t the first one visited wins.
+constexpr int kStackSize = 64;
+
+template <bool ANY>
+LJ_HD bool trace2(const DevNode2 *nodes, const DevPrim *prims, V3 o, V3 d, float tnear, float tfar, Hit &hit) {
+    hit.prim = kNoHit;
+    hit.t = tfar;
+    hit.u = hit.v = 0;
+    if (!(tnear <= tfar)) return false;
+    V3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    int stack[kStackSize];
+    int sp = 0;
+    int node = 0;
+    const int kSentinel = 0x7fffffff;
+    stack[sp++] = kSentinel;
+    while (node != kSentinel) {
+        if (node >= 0) {
+            V4 n0 = ld4(&nodes[node].n0), n1 = ld4(&nodes[node].n1);
+            V4 n2 = ld4(&nodes[node].n2), n3 = ld4(&nodes[node].n3);
+            float c0lox = (n0.x - o.x) * inv.x, c0hix = (n0.y - o.x) * inv.x;
+            float c0loy = (n0.z - o.y) * inv.y, c0hiy = (n0.w - o.y) * inv.y;
+            float c0loz = (n2.x - o.z) * inv.z, c0hiz = (n2.y - o.z) * inv.z;
+            float c1lox = (n1.x - o.x) * inv.x, c1hix = (n1.y - o.x) * inv.x;
+            float c1loy = (n1.z - o.y) * inv.y, c1hiy = (n1.w - o.y) * inv.y;
+            float c1loz = (n2.z - o.z) * inv.z, c1hiz = (n2.w - o.z) * inv.z;
+            float t0n = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), tnear));
+            float t0f = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), hit.t));
+            float t1n = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), tnear));
+            float t1f = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), hit.t));
+            // conservative: widen the far side by 2 ulp (Ize, "Robust BVH ray traversal")
+            bool h0 = t0n <= t0f * 1.0000004f;
+            bool h1 = t1n <= t1f * 1.0000004f;
+            int c0 = (int)f2u(n3.x), c1 = (int)f2u(n3.y);
+            if (h0 && h1) {
+                bool swap = t1n < t0n;
+                node = swap ? c1 : c0;
+                if (sp < kStackSize) stack[sp++] = swap ? c0 : c1;
+            } else if (h0) {
+                node = c0;
+            } else if (h1) {
+                node = c1;
+            } else {
+                node = stack[--sp];
+            }
+        } else {
+            int v = ~node;
+            int first = v >> 3, count = (v & 7) + 1;
+            for (int i = 0; i < count; i++) {
+                float t, uu, vv;
+                if (hit_prim(prims, first + i, o, d, tnear, hit.t, t, uu, vv)) {
+                    if (ANY) { hit.prim = first + i; hit.t = t; return true; }
+                    if (t < hit.t || hit.prim == kNoHit) {
+                        hit.t = t; hit.u = uu; hit.v = vv; hit.prim = first + i;
+                    }
+                }
+            }
+            node = stack[--sp];
+        }
+    }
+    return hit.prim != kNoHit;
+}
+
+}  // namespace lj

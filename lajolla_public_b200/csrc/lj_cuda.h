@@ -1,0 +1,31 @@
+// lj_cuda.h -- the one place that names the CUDA runtime.
+//
+// Product build (nvcc, sm_100a): plain cuda_runtime.h and a launch macro.
+// tests/hostsim build (g++, -DLJ_HOSTSIM): tests/hostsim/cuda_sim.h maps the handful of runtime
+// calls onto malloc/memcpy and runs each kernel launch as a serial loop with "warps" of one thread,
+// so the orchestration code (queues, counters, BVH build order) can be unit-tested on the GPU-less
+// authoring box.  The sim is test infrastructure: it is never built into libljb200.so, never loaded
+// by the lajolla_public_b200 package and never benchmarked.
+#pragma once
+
+#if defined(LJ_HOSTSIM)
+#include "cuda_sim.h"
+#else
+#include <cuda_runtime.h>
+#define LJ_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#define LJ_LANE() ((int)(threadIdx.x & 31))
+#define LJ_GRID_CONSTANT __grid_constant__
+__device__ __forceinline__ float lj_warp_min(float x) {
+    for (int o = 16; o > 0; o >>= 1) x = fminf(x, __shfl_xor_sync(0xffffffffu, x, o));
+    return x;
+}
+__device__ __forceinline__ float lj_warp_max(float x) {
+    for (int o = 16; o > 0; o >>= 1) x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, o));
+    return x;
+}
+__device__ __forceinline__ double lj_warp_sum(double x) {
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+__device__ __forceinline__ int lj_float_as_int(float f) { return __float_as_int(f); }
+#endif

@@ -1,0 +1,502 @@
+// lj_materials.h -- eval / pdf_sample_bsdf / sample_bsdf for the nine Material alternatives.
+// fp32 restatement of the reference's material.cpp:4-11,90-123, microfacet.h:23-114,
+// materials/lambertian.inl, roughplastic.inl, roughdielectric.inl.  The six Disney alternatives are
+// homework stubs upstream (materials/disney_*.inl return zero); they follow handouts/homework1.tex
+// (equation cites inline) and keep the frame-flip / below-surface early-outs of the stub files.
+// eval() returns BSDF * |n . dir_out| (material.h:119-131).  Directions point away from the surface.
+#pragma once
+#include "lj_shapes.h"
+#include "lj_texture.h"
+
+namespace lj {
+
+struct BsdfSample { V3 dir_out; float eta, roughness; };  // material.h:133-138
+
+// material.cpp:4-11
+LJ_HD V3 sample_cos_hemisphere(V2 u) {
+    float phi = kTwoPi * u.x;
+    float tmp = sqrtf(clampf(1 - u.y, 0.f, 1.f));
+    return mk3(cosf(phi) * tmp, sinf(phi) * tmp, sqrtf(clampf(u.y, 0.f, 1.f)));
+}
+
+LJ_HD float pow5(float x) { float x2 = x * x; return x2 * x2 * x; }
+
+// microfacet.h:23-27 (the pow(max(1-c,0),5))
+LJ_HD float schlick_weight(float cos_theta) { return pow5(fmaxf(1 - cos_theta, 0.f)); }
+LJ_HD V3 schlick_fresnel3(V3 F0, float cos_theta) { return F0 + (mk3(1) - F0) * schlick_weight(cos_theta); }
+LJ_HD float schlick_fresnel1(float F0, float cos_theta) { return F0 + (1 - F0) * schlick_weight(cos_theta); }
+
+// microfacet.h:34-55
+LJ_HD float fresnel_dielectric2(float n_dot_i, float n_dot_t, float eta) {
+    float rs = (n_dot_i - eta * n_dot_t) / (n_dot_i + eta * n_dot_t);
+    float rp = (eta * n_dot_i - n_dot_t) / (eta * n_dot_i + n_dot_t);
+    return (rs * rs + rp * rp) / 2;
+}
+LJ_HD float fresnel_dielectric(float n_dot_i, float eta) {
+    float n_dot_t_sq = 1 - (1 - n_dot_i * n_dot_i) / (eta * eta);
+    if (n_dot_t_sq < 0) return 1;
+    return fresnel_dielectric2(fabsf(n_dot_i), sqrtf(n_dot_t_sq), eta);
+}
+
+// microfacet.h:57-81
+LJ_HD float GTR2(float n_dot_h, float roughness) {
+    float alpha = roughness * roughness;
+    float a2 = alpha * alpha;
+    float t = 1 + (a2 - 1) * n_dot_h * n_dot_h;
+    return a2 / (kPi * t * t);
+}
+LJ_HD float smith_masking_gtr2(V3 v, float roughness) {
+    float alpha = roughness * roughness;
+    float a2 = alpha * alpha;
+    float Lambda = (-1 + sqrtf(1 + (v.x * v.x * a2 + v.y * v.y * a2) / (v.z * v.z))) / 2;
+    return 1 / (1 + Lambda);
+}
+
+// microfacet.h:85-114 (Heitz 2018), generalised to (alpha_x, alpha_y) for the Disney lobes
+// (homework1.tex:251); alpha_x == alpha_y reproduces the reference's isotropic routine.
+LJ_HD V3 sample_visible_normals(V3 local_dir_in, float ax, float ay, V2 u) {
+    bool flipped = local_dir_in.z < 0;
+    if (flipped) local_dir_in = -local_dir_in;
+    V3 hemi = normalize(mk3(ax * local_dir_in.x, ay * local_dir_in.y, local_dir_in.z));
+    float r = sqrtf(u.x);
+    float phi = 2 * kPi * u.y;
+    float t1 = r * cosf(phi);
+    float t2 = r * sinf(phi);
+    float s = (1 + hemi.z) / 2;
+    t2 = (1 - s) * sqrtf(1 - t1 * t1) + s * t2;
+    V3 disk = mk3(t1, t2, sqrtf(fmaxf(0.f, 1 - t1 * t1 - t2 * t2)));
+    Frame hf = make_frame(hemi);
+    V3 hn = to_world(hf, disk);
+    V3 n = normalize(mk3(ax * hn.x, ay * hn.y, fmaxf(0.f, hn.z)));
+    return flipped ? -n : n;
+}
+
+// Frame conventions shared by every lobe.
+LJ_HD Frame frame_reflective(const Vertex &vx, V3 dir_in) {  // lambertian.inl:10-13
+    Frame f = vx.shading_frame;
+    if (dot(f.n, dir_in) < 0) f = flip(f);
+    return f;
+}
+LJ_HD Frame frame_transmissive(const Vertex &vx, V3 dir_in) {  // roughdielectric.inl:6-9
+    Frame f = vx.shading_frame;
+    if (dot(f.n, dir_in) * dot(vx.geometric_normal, dir_in) < 0) f = flip(f);
+    return f;
+}
+LJ_HD bool below_surface(const Vertex &vx, V3 dir_in, V3 dir_out) {  // lambertian.inl:2-6
+    return dot(vx.geometric_normal, dir_in) < 0 || dot(vx.geometric_normal, dir_out) < 0;
+}
+
+// ============================================================== Lambertian (lambertian.inl)
+LJ_HD V3 lambertian_eval(V3 R, const Vertex &vx, V3 wi, V3 wo) {
+    if (below_surface(vx, wi, wo)) return mk3(0);
+    Frame f = frame_reflective(vx, wi);
+    return R * (fmaxf(dot(f.n, wo), 0.f) / kPi);
+}
+LJ_HD float lambertian_pdf(const Vertex &vx, V3 wi, V3 wo) {
+    if (below_surface(vx, wi, wo)) return 0;
+    Frame f = frame_reflective(vx, wi);
+    return fmaxf(dot(f.n, wo), 0.f) / kPi;
+}
+LJ_HD bool lambertian_sample(const Vertex &vx, V3 wi, V2 u, BsdfSample &s) {
+    if (dot(vx.geometric_normal, wi) < 0) return false;
+    Frame f = frame_reflective(vx, wi);
+    s.dir_out = to_world(f, sample_cos_hemisphere(u));
+    s.eta = 0;
+    s.roughness = 1;
+    return true;
+}
+
+// ============================================================== RoughPlastic (roughplastic.inl)
+LJ_HD V3 roughplastic_eval(V3 Kd, V3 Ks, float roughness, float eta, const Vertex &vx, V3 wi, V3 wo) {
+    if (below_surface(vx, wi, wo)) return mk3(0);
+    Frame f = frame_reflective(vx, wi);
+    V3 h = normalize(wi + wo);
+    float n_dot_h = dot(f.n, h), n_dot_in = dot(f.n, wi), n_dot_out = dot(f.n, wo);
+    if (n_dot_out <= 0 || n_dot_h <= 0) return mk3(0);
+    roughness = clampf(roughness, 0.01f, 1.f);
+    float F_o = fresnel_dielectric(dot(h, wo), eta);
+    float D = GTR2(n_dot_h, roughness);
+    float G = smith_masking_gtr2(to_local(f, wi), roughness) * smith_masking_gtr2(to_local(f, wo), roughness);
+    V3 spec = Ks * ((G * F_o * D) / (4 * n_dot_in * n_dot_out));
+    float F_i = fresnel_dielectric(dot(h, wi), eta);
+    V3 diff = Kd * ((1 - F_o) * (1 - F_i) / kPi);
+    return (spec + diff) * n_dot_out;
+}
+LJ_HD float roughplastic_pdf(V3 Kd, V3 Ks, float roughness, const Vertex &vx, V3 wi, V3 wo) {
+    if (below_surface(vx, wi, wo)) return 0;
+    Frame f = frame_reflective(vx, wi);
+    V3 h = normalize(wi + wo);
+    float n_dot_in = dot(f.n, wi), n_dot_out = dot(f.n, wo), n_dot_h = dot(f.n, h);
+    if (n_dot_out <= 0 || n_dot_h <= 0) return 0;
+    float lS = luminance(Ks), lR = luminance(Kd);
+    if (lS + lR <= 0) return 0;
+    roughness = clampf(roughness, 0.01f, 1.f);
+    float spec_prob = lS / (lS + lR);
+    float diff_prob = 1 - spec_prob;
+    float G = smith_masking_gtr2(to_local(f, wi), roughness);
+    float D = GTR2(n_dot_h, roughness);
+    spec_prob *= (G * D) / (4 * n_dot_in);
+    diff_prob *= n_dot_out / kPi;
+    return spec_prob + diff_prob;
+}
+LJ_HD bool roughplastic_sample(V3 Kd, V3 Ks, float roughness, const Vertex &vx, V3 wi, V2 u, float w, BsdfSample &s) {
+    if (dot(vx.geometric_normal, wi) < 0) return false;
+    Frame f = frame_reflective(vx, wi);
+    float lS = luminance(Ks), lR = luminance(Kd);
+    if (lS + lR <= 0) return false;
+    float spec_prob = lS / (lS + lR);
+    if (w < spec_prob) {
+        V3 li = to_local(f, wi);
+        roughness = clampf(roughness, 0.01f, 1.f);
+        float alpha = roughness * roughness;
+        V3 h = to_world(f, sample_visible_normals(li, alpha, alpha, u));
+        s.dir_out = normalize(-wi + 2 * dot(wi, h) * h);
+        s.eta = 0;
+        s.roughness = roughness;
+    } else {
+        s.dir_out = to_world(f, sample_cos_hemisphere(u));
+        s.eta = 0;
+        s.roughness = 1;
+    }
+    return true;
+}
+
+// ===================================================== RoughDielectric (roughdielectric.inl)
+// Shared with DisneyGlass: Cr / Ct are the reflection / transmission tints, (ax, ay) the GGX
+// alphas, D and G evaluated by the anisotropic forms below (isotropic when ax == ay).
+LJ_HD float ggx_aniso_D(V3 hl, float ax, float ay) {  // homework1.tex:197-201
+    float t = hl.x * hl.x / (ax * ax) + hl.y * hl.y / (ay * ay) + hl.z * hl.z;
+    return 1 / (kPi * ax * ay * t * t);
+}
+LJ_HD float smith_aniso_G1(V3 wl, float ax, float ay) {  // homework1.tex:213-220
+    float Lambda = (sqrtf(1 + ((wl.x * ax) * (wl.x * ax) + (wl.y * ay) * (wl.y * ay)) / (wl.z * wl.z)) - 1) / 2;
+    return 1 / (1 + Lambda);
+}
+
+LJ_HD V3 dielectric_eval(V3 Cr, V3 Ct, float ax, float ay, float mat_eta, const Vertex &vx, V3 wi, V3 wo, int transport) {
+    bool reflect = dot(vx.geometric_normal, wi) * dot(vx.geometric_normal, wo) > 0;
+    Frame f = frame_transmissive(vx, wi);
+    float eta = dot(vx.geometric_normal, wi) > 0 ? mat_eta : 1 / mat_eta;
+    V3 h = reflect ? normalize(wi + wo) : normalize(wi + wo * eta);
+    if (dot(h, f.n) < 0) h = -h;
+    float h_dot_in = dot(h, wi);
+    float F = fresnel_dielectric(h_dot_in, eta);
+    float D = ggx_aniso_D(to_local(f, h), ax, ay);
+    float G = smith_aniso_G1(to_local(f, wi), ax, ay) * smith_aniso_G1(to_local(f, wo), ax, ay);
+    if (reflect) return Cr * ((F * D * G) / (4 * fabsf(dot(f.n, wi))));
+    float eta_factor = transport == 0 ? (1 / (eta * eta)) : 1;  // roughdielectric.inl:64
+    float h_dot_out = dot(h, wo);
+    float sqrt_denom = h_dot_in + eta * h_dot_out;
+    return Ct * ((eta_factor * (1 - F) * D * G * eta * eta * fabsf(h_dot_out * h_dot_in)) /
+                 (fabsf(dot(f.n, wi)) * sqrt_denom * sqrt_denom));
+}
+LJ_HD float dielectric_pdf(float ax, float ay, float mat_eta, const Vertex &vx, V3 wi, V3 wo) {
+    bool reflect = dot(vx.geometric_normal, wi) * dot(vx.geometric_normal, wo) > 0;
+    Frame f = frame_transmissive(vx, wi);
+    float eta = dot(vx.geometric_normal, wi) > 0 ? mat_eta : 1 / mat_eta;
+    V3 h = reflect ? normalize(wi + wo) : normalize(wi + wo * eta);
+    if (dot(h, f.n) < 0) h = -h;
+    float h_dot_in = dot(h, wi);
+    float F = fresnel_dielectric(h_dot_in, eta);
+    float D = ggx_aniso_D(to_local(f, h), ax, ay);
+    float G_in = smith_aniso_G1(to_local(f, wi), ax, ay);
+    if (reflect) return (F * D * G_in) / (4 * fabsf(dot(f.n, wi)));
+    float h_dot_out = dot(h, wo);
+    float sqrt_denom = h_dot_in + eta * h_dot_out;
+    float dh_dout = eta * eta * h_dot_out / (sqrt_denom * sqrt_denom);
+    return (1 - F) * D * G_in * fabsf(dh_dout * h_dot_in / dot(f.n, wi));
+}
+LJ_HD bool dielectric_sample(float ax, float ay, float roughness, float mat_eta, const Vertex &vx, V3 wi, V2 u, float w, BsdfSample &s) {
+    float eta = dot(vx.geometric_normal, wi) > 0 ? mat_eta : 1 / mat_eta;
+    Frame f = frame_transmissive(vx, wi);
+    V3 h = to_world(f, sample_visible_normals(to_local(f, wi), ax, ay, u));
+    if (dot(h, f.n) < 0) h = -h;
+    float h_dot_in = dot(h, wi);
+    float F = fresnel_dielectric(h_dot_in, eta);
+    if (w <= F) {
+        s.dir_out = normalize(-wi + 2 * dot(wi, h) * h);
+        s.eta = 0;
+        s.roughness = roughness;
+        return true;
+    }
+    float h_dot_out_sq = 1 - (1 - h_dot_in * h_dot_in) / (eta * eta);
+    if (h_dot_out_sq <= 0) return false;
+    if (h_dot_in < 0) h = -h;
+    float h_dot_out = sqrtf(h_dot_out_sq);
+    s.dir_out = -wi / eta + (fabsf(h_dot_in) / eta - h_dot_out) * h;
+    s.eta = eta;
+    s.roughness = roughness;
+    return true;
+}
+
+// ========================================================================== Disney lobes
+LJ_HD void disney_alphas(float roughness, float anisotropic, float &ax, float &ay) {  // homework1.tex:204-210
+    float aspect = sqrtf(1 - 0.9f * anisotropic);
+    ax = fmaxf(1e-4f, roughness * roughness / aspect);
+    ay = fmaxf(1e-4f, roughness * roughness * aspect);
+}
+LJ_HD V3 disney_tint(V3 base) {  // homework1.tex:417
+    float l = luminance(base);
+    return l > 0 ? base / l : mk3(1);
+}
+
+// diffuse + subsurface, homework1.tex:100-135
+LJ_HD V3 disney_diffuse_eval(V3 base, float roughness, float subsurface, const Vertex &vx, V3 wi, V3 wo) {
+    if (below_surface(vx, wi, wo)) return mk3(0);
+    Frame f = frame_reflective(vx, wi);
+    V3 h = normalize(wi + wo);
+    float n_in = fabsf(dot(f.n, wi)), n_out = fabsf(dot(f.n, wo));
+    float h_out = fabsf(dot(h, wo));
+    float FD90 = 0.5f + 2 * roughness * h_out * h_out;
+    float FD_in = 1 + (FD90 - 1) * pow5(1 - n_in), FD_out = 1 + (FD90 - 1) * pow5(1 - n_out);
+    V3 base_diffuse = base * (FD_in * FD_out * n_out / kPi);
+    float FSS90 = roughness * h_out * h_out;
+    float FSS_in = 1 + (FSS90 - 1) * pow5(1 - n_in), FSS_out = 1 + (FSS90 - 1) * pow5(1 - n_out);
+    float denom = n_in + n_out;
+    float ss_term = denom > 0 ? (FSS_in * FSS_out * (1 / denom - 0.5f) + 0.5f) : 0.5f;
+    V3 ss = base * (1.25f * ss_term * n_out / kPi);
+    return (1 - subsurface) * base_diffuse + subsurface * ss;
+}
+// cosine-hemisphere sampling (homework1.tex:166): pdf and sample are Lambertian's.
+
+// metal, homework1.tex:182-222; F is supplied so the full BSDF can pass its modified Fresnel.
+LJ_HD bool disney_metal_geom(float ax, float ay, const Vertex &vx, V3 wi, V3 wo, V3 &h, float &D, float &G_in, float &G_out, float &n_in) {
+    if (below_surface(vx, wi, wo)) return false;
+    Frame f = frame_reflective(vx, wi);
+    h = normalize(wi + wo);
+    n_in = dot(f.n, wi);
+    if (dot(f.n, wo) <= 0 || dot(f.n, h) <= 0 || n_in <= 0) return false;
+    D = ggx_aniso_D(to_local(f, h), ax, ay);
+    G_in = smith_aniso_G1(to_local(f, wi), ax, ay);
+    G_out = smith_aniso_G1(to_local(f, wo), ax, ay);
+    return true;
+}
+LJ_HD V3 disney_metal_eval(V3 F0, float ax, float ay, const Vertex &vx, V3 wi, V3 wo) {
+    V3 h; float D, Gi, Go, n_in;
+    if (!disney_metal_geom(ax, ay, vx, wi, wo, h, D, Gi, Go, n_in)) return mk3(0);
+    V3 F = schlick_fresnel3(F0, fabsf(dot(h, wo)));
+    return F * (D * Gi * Go / (4 * fabsf(n_in)));
+}
+LJ_HD float disney_metal_pdf(float ax, float ay, const Vertex &vx, V3 wi, V3 wo) {
+    V3 h; float D, Gi, Go, n_in;
+    if (!disney_metal_geom(ax, ay, vx, wi, wo, h, D, Gi, Go, n_in)) return 0;
+    return D * Gi / (4 * fabsf(n_in));
+}
+LJ_HD bool disney_metal_sample(float ax, float ay, float roughness, const Vertex &vx, V3 wi, V2 u, BsdfSample &s) {
+    if (dot(vx.geometric_normal, wi) < 0) return false;
+    Frame f = frame_reflective(vx, wi);
+    V3 h = to_world(f, sample_visible_normals(to_local(f, wi), ax, ay, u));
+    s.dir_out = normalize(-wi + 2 * dot(wi, h) * h);
+    s.eta = 0;
+    s.roughness = roughness;
+    return true;
+}
+
+// clearcoat, homework1.tex:267-327
+LJ_HD float clearcoat_alpha(float gloss) { return (1 - gloss) * 0.1f + gloss * 0.001f; }
+LJ_HD float clearcoat_D(float a2, float hlz) { return (a2 - 1) / (kPi * logf(a2) * (1 + (a2 - 1) * hlz * hlz)); }
+LJ_HD float disney_clearcoat_eval(float gloss, const Vertex &vx, V3 wi, V3 wo) {
+    if (below_surface(vx, wi, wo)) return 0;
+    Frame f = frame_reflective(vx, wi);
+    V3 h = normalize(wi + wo);
+    float n_in = dot(f.n, wi);
+    if (dot(f.n, wo) <= 0 || dot(f.n, h) <= 0 || n_in <= 0) return 0;
+    float ag = clearcoat_alpha(gloss);
+    float Fc = schlick_fresnel1(0.04f, fabsf(dot(h, wo)));  // R0(eta = 1.5)
+    float Dc = clearcoat_D(ag * ag, dot(f.n, h));
+    float Gc = smith_aniso_G1(to_local(f, wi), 0.25f, 0.25f) * smith_aniso_G1(to_local(f, wo), 0.25f, 0.25f);
+    return Fc * Dc * Gc / (4 * fabsf(n_in));
+}
+LJ_HD float disney_clearcoat_pdf(float gloss, const Vertex &vx, V3 wi, V3 wo) {
+    if (below_surface(vx, wi, wo)) return 0;
+    Frame f = frame_reflective(vx, wi);
+    V3 h = normalize(wi + wo);
+    float n_h = dot(f.n, h);
+    if (dot(f.n, wo) <= 0 || n_h <= 0) return 0;
+    float ag = clearcoat_alpha(gloss);
+    return clearcoat_D(ag * ag, n_h) * fabsf(n_h) / (4 * fabsf(dot(h, wo)));
+}
+LJ_HD bool disney_clearcoat_sample(float gloss, const Vertex &vx, V3 wi, V2 u, BsdfSample &s) {
+    if (dot(vx.geometric_normal, wi) < 0) return false;
+    Frame f = frame_reflective(vx, wi);
+    float ag = clearcoat_alpha(gloss);
+    float a2 = ag * ag;
+    float cos_e = sqrtf(clampf((1 - powf(a2, 1 - u.x)) / (1 - a2), 0.f, 1.f));
+    float sin_e = sqrtf(fmaxf(0.f, 1 - cos_e * cos_e));
+    float az = 2 * kPi * u.y;
+    V3 h = to_world(f, mk3(sin_e * cosf(az), sin_e * sinf(az), cos_e));
+    s.dir_out = normalize(-wi + 2 * dot(wi, h) * h);
+    s.eta = 0;
+    s.roughness = sqrtf(ag);
+    return true;
+}
+
+// sheen, homework1.tex:412-425 (cosine-hemisphere sampled)
+LJ_HD V3 disney_sheen_eval(V3 base, float sheen_tint, const Vertex &vx, V3 wi, V3 wo) {
+    if (below_surface(vx, wi, wo)) return mk3(0);
+    Frame f = frame_reflective(vx, wi);
+    V3 h = normalize(wi + wo);
+    V3 Csheen = mk3(1 - sheen_tint) + sheen_tint * disney_tint(base);
+    return Csheen * (pow5(1 - fabsf(dot(h, wo))) * fabsf(dot(f.n, wo)));
+}
+
+// ========================================================================== dispatch
+struct MatParams {  // textures of one material evaluated at one vertex
+    V3 c0, c1;      // slot 0 / slot 1 colours
+    float p[kNumTexSlots];
+};
+
+LJ_HD V3 mat_tex3(const DevScene &sc, const DevMaterial &m, int slot, const Vertex &vx) {
+    return eval_tex3(sc, m.tex[slot], vx.uv, vx.uv_screen_size);
+}
+LJ_HD float mat_tex1(const DevScene &sc, const DevMaterial &m, int slot, const Vertex &vx) {
+    return eval_tex1(sc, m.tex[slot], vx.uv, vx.uv_screen_size);
+}
+
+struct DisneyParams {
+    V3 base;
+    float st, metallic, subsurface, specular, roughness, stint, aniso, sheen, sheen_tint, cc, cc_gloss, eta;
+};
+LJ_HD DisneyParams disney_params(const DevScene &sc, const DevMaterial &m, const Vertex &vx) {
+    DisneyParams p;
+    p.base = mat_tex3(sc, m, 0, vx);
+    p.subsurface = mat_tex1(sc, m, 1, vx);
+    p.roughness = clampf(mat_tex1(sc, m, 2, vx), 0.01f, 1.f);
+    p.aniso = mat_tex1(sc, m, 3, vx);
+    p.cc_gloss = mat_tex1(sc, m, 4, vx);
+    p.sheen_tint = mat_tex1(sc, m, 5, vx);
+    p.st = mat_tex1(sc, m, 6, vx);
+    p.metallic = mat_tex1(sc, m, 7, vx);
+    p.specular = mat_tex1(sc, m, 8, vx);
+    p.stint = mat_tex1(sc, m, 9, vx);
+    p.sheen = mat_tex1(sc, m, 10, vx);
+    p.cc = mat_tex1(sc, m, 11, vx);
+    p.eta = m.eta;
+    return p;
+}
+// modified metal Fresnel base C0, homework1.tex:478-482
+LJ_HD V3 disney_C0(const DisneyParams &p) {
+    float r0 = (p.eta - 1) * (p.eta - 1) / ((p.eta + 1) * (p.eta + 1));
+    V3 Ks = mk3(1 - p.stint) + p.stint * disney_tint(p.base);
+    return (p.specular * r0 * (1 - p.metallic)) * Ks + p.metallic * p.base;
+}
+LJ_HD void disney_weights(const DisneyParams &p, float &dw, float &mw, float &gw, float &cw) {  // homework1.tex:534-541
+    dw = (1 - p.metallic) * (1 - p.st);
+    mw = 1 - p.st * (1 - p.metallic);
+    gw = (1 - p.metallic) * p.st;
+    cw = 0.25f * p.cc;
+}
+
+LJ_HD V3 disney_bsdf_eval(const DisneyParams &p, const Vertex &vx, V3 wi, V3 wo, int transport) {
+    float ax, ay;
+    disney_alphas(p.roughness, p.aniso, ax, ay);
+    V3 glass = dielectric_eval(p.base, sqrt3(p.base), ax, ay, p.eta, vx, wi, wo, transport);
+    float gscale = (1 - p.metallic) * p.st;
+    if (dot(vx.geometric_normal, wi) <= 0) return gscale * glass;  // inside: glass only (:486-494)
+    V3 f = gscale * glass;
+    f += ((1 - p.st) * (1 - p.metallic)) * disney_diffuse_eval(p.base, p.roughness, p.subsurface, vx, wi, wo);
+    f += ((1 - p.metallic) * p.sheen) * disney_sheen_eval(p.base, p.sheen_tint, vx, wi, wo);
+    f += (1 - p.st * (1 - p.metallic)) * disney_metal_eval(disney_C0(p), ax, ay, vx, wi, wo);
+    f += mk3(0.25f * p.cc * disney_clearcoat_eval(p.cc_gloss, vx, wi, wo));
+    return f;
+}
+LJ_HD float disney_bsdf_pdf(const DisneyParams &p, const Vertex &vx, V3 wi, V3 wo) {
+    float ax, ay;
+    disney_alphas(p.roughness, p.aniso, ax, ay);
+    float pg = dielectric_pdf(ax, ay, p.eta, vx, wi, wo);
+    if (dot(vx.geometric_normal, wi) <= 0) return pg;
+    float dw, mw, gw, cw;
+    disney_weights(p, dw, mw, gw, cw);
+    float total = dw + mw + gw + cw;
+    if (total <= 0) return 0;
+    float pdf = dw * lambertian_pdf(vx, wi, wo) + mw * disney_metal_pdf(ax, ay, vx, wi, wo) + gw * pg +
+                cw * disney_clearcoat_pdf(p.cc_gloss, vx, wi, wo);
+    return pdf / total;
+}
+LJ_HD bool disney_bsdf_sample(const DisneyParams &p, const Vertex &vx, V3 wi, V2 u, float w, BsdfSample &s) {
+    float ax, ay;
+    disney_alphas(p.roughness, p.aniso, ax, ay);
+    if (dot(vx.geometric_normal, wi) <= 0) return dielectric_sample(ax, ay, p.roughness, p.eta, vx, wi, u, w, s);
+    float dw, mw, gw, cw;
+    disney_weights(p, dw, mw, gw, cw);
+    float total = dw + mw + gw + cw;
+    if (total <= 0) return false;
+    dw /= total; mw /= total; gw /= total;
+    if (w < dw) return lambertian_sample(vx, wi, u, s);
+    if (w < dw + mw) return disney_metal_sample(ax, ay, p.roughness, vx, wi, u, s);
+    if (w < dw + mw + gw) {
+        float w2 = (w - (dw + mw)) / gw;  // rescale for the reflect/refract pick (homework1.tex:548)
+        return dielectric_sample(ax, ay, p.roughness, p.eta, vx, wi, u, w2, s);
+    }
+    return disney_clearcoat_sample(p.cc_gloss, vx, wi, u, s);
+}
+
+// material.cpp:90-123: the three entry points, switch instead of std::visit.
+LJ_HD V3 bsdf_eval(const DevScene &sc, const DevMaterial &m, V3 wi, V3 wo, const Vertex &vx, int transport) {
+    switch (m.type) {
+        case 0: return lambertian_eval(mat_tex3(sc, m, 0, vx), vx, wi, wo);
+        case 1: return roughplastic_eval(mat_tex3(sc, m, 0, vx), mat_tex3(sc, m, 1, vx), mat_tex1(sc, m, 2, vx), m.eta, vx, wi, wo);
+        case 2: {
+            float r = clampf(mat_tex1(sc, m, 2, vx), 0.01f, 1.f);
+            return dielectric_eval(mat_tex3(sc, m, 1, vx), mat_tex3(sc, m, 0, vx), r * r, r * r, m.eta, vx, wi, wo, transport);
+        }
+        case 3: return disney_diffuse_eval(mat_tex3(sc, m, 0, vx), clampf(mat_tex1(sc, m, 2, vx), 0.01f, 1.f), mat_tex1(sc, m, 1, vx), vx, wi, wo);
+        case 4: {
+            float ax, ay;
+            disney_alphas(clampf(mat_tex1(sc, m, 2, vx), 0.01f, 1.f), mat_tex1(sc, m, 3, vx), ax, ay);
+            return disney_metal_eval(mat_tex3(sc, m, 0, vx), ax, ay, vx, wi, wo);
+        }
+        case 5: {
+            float ax, ay;
+            disney_alphas(clampf(mat_tex1(sc, m, 2, vx), 0.01f, 1.f), mat_tex1(sc, m, 3, vx), ax, ay);
+            V3 base = mat_tex3(sc, m, 0, vx);
+            return dielectric_eval(base, sqrt3(base), ax, ay, m.eta, vx, wi, wo, transport);
+        }
+        case 6: return mk3(disney_clearcoat_eval(mat_tex1(sc, m, 4, vx), vx, wi, wo));
+        case 7: return disney_sheen_eval(mat_tex3(sc, m, 0, vx), mat_tex1(sc, m, 5, vx), vx, wi, wo);
+        case 8: return disney_bsdf_eval(disney_params(sc, m, vx), vx, wi, wo, transport);
+    }
+    return mk3(0);
+}
+
+LJ_HD float bsdf_pdf(const DevScene &sc, const DevMaterial &m, V3 wi, V3 wo, const Vertex &vx) {
+    switch (m.type) {
+        case 0: case 3: case 7: return lambertian_pdf(vx, wi, wo);
+        case 1: return roughplastic_pdf(mat_tex3(sc, m, 0, vx), mat_tex3(sc, m, 1, vx), mat_tex1(sc, m, 2, vx), vx, wi, wo);
+        case 2: {
+            float r = clampf(mat_tex1(sc, m, 2, vx), 0.01f, 1.f);
+            return dielectric_pdf(r * r, r * r, m.eta, vx, wi, wo);
+        }
+        case 4: case 5: {
+            float ax, ay;
+            disney_alphas(clampf(mat_tex1(sc, m, 2, vx), 0.01f, 1.f), mat_tex1(sc, m, 3, vx), ax, ay);
+            return m.type == 4 ? disney_metal_pdf(ax, ay, vx, wi, wo) : dielectric_pdf(ax, ay, m.eta, vx, wi, wo);
+        }
+        case 6: return disney_clearcoat_pdf(mat_tex1(sc, m, 4, vx), vx, wi, wo);
+        case 8: return disney_bsdf_pdf(disney_params(sc, m, vx), vx, wi, wo);
+    }
+    return 0;
+}
+
+LJ_HD bool bsdf_sample(const DevScene &sc, const DevMaterial &m, V3 wi, const Vertex &vx, V2 u, float w, BsdfSample &s) {
+    switch (m.type) {
+        case 0: case 3: case 7: return lambertian_sample(vx, wi, u, s);
+        case 1: return roughplastic_sample(mat_tex3(sc, m, 0, vx), mat_tex3(sc, m, 1, vx), mat_tex1(sc, m, 2, vx), vx, wi, u, w, s);
+        case 2: {
+            float r = clampf(mat_tex1(sc, m, 2, vx), 0.01f, 1.f);
+            return dielectric_sample(r * r, r * r, r, m.eta, vx, wi, u, w, s);
+        }
+        case 4: case 5: {
+            float r = clampf(mat_tex1(sc, m, 2, vx), 0.01f, 1.f);
+            float ax, ay;
+            disney_alphas(r, mat_tex1(sc, m, 3, vx), ax, ay);
+            if (m.type == 4) return disney_metal_sample(ax, ay, r, vx, wi, u, s);
+            return dielectric_sample(ax, ay, r, m.eta, vx, wi, u, w, s);
+        }
+        case 6: return disney_clearcoat_sample(mat_tex1(sc, m, 4, vx), vx, wi, u, s);
+        case 8: return disney_bsdf_sample(disney_params(sc, m, vx), vx, wi, u, w, s);
+    }
+    return false;
+}
+
+}  // namespace lj

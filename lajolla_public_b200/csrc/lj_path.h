@@ -1,0 +1,250 @@
+// lj_path.h -- the per-sample radiance estimator of the reference's path_tracing.h:7-325, cut into
+// wavefront stages.  One call of path_tracing() becomes: generate (path_tracing.h:10-14) ->
+// [extend -> shade -> shadow]* where each shade() is "the second half of loop iteration k"
+// (MIS-weighted emission at the vertex the extension ray found, :242-307, Russian roulette,
+// :311-318) followed by "the first half of iteration k+1" (NEE sample, :94-207, BSDF sample,
+// :209-237).  Per-path random numbers are drawn in exactly the order of the reference loop, from
+// a private PCG32 stream.  Path records live in HBM as a structure of 16-byte arrays.
+#pragma once
+#include "lj_camera.h"
+#include "lj_lights.h"
+#include "lj_materials.h"
+#include "lj_pcg.h"
+
+namespace lj {
+
+struct U4 { uint32_t x, y, z, w; };
+
+// Structure-of-arrays path pool: every field is one 16-byte record per path slot.
+struct PathPool {
+    V4 *ray_o;  // org.xyz, tnear
+    V4 *ray_d;  // dir.xyz, tfar
+    V4 *hit;    // t, u, v, bits(prim)           (written by extend)
+    V4 *thr;    // throughput.xyz (f/pdf of the last bounce folded in), last bsdf pdf (solid angle; <0 = camera ray)
+    V4 *rad;    // radiance.xyz accumulated by this path, rr_prob for the pending vertex
+    V4 *sh_d;   // shadow dir.xyz, tfar (<0: no shadow ray)
+    V4 *sh_c;   // NEE contribution if unoccluded .xyz, -
+    V4 *meta;   // bits(pixel), bits(nv | flags<<16), bits(rng lo), bits(rng hi)
+    V4 *aux;    // eta_scale, ray spread, bits(sample index), bits(medium id)
+    int capacity;
+};
+
+constexpr uint32_t kAlive = 1u << 16;     // slot holds a path whose extension ray is pending
+constexpr uint32_t kOccupied = 1u << 17;  // slot holds radiance not yet flushed to the film
+
+struct PathState {
+    V3 o; float tnear;
+    V3 d; float tfar;
+    Hit hit;
+    V3 T; float pdf_sa;
+    V3 L; float rr_prob;
+    V3 sh_d; float sh_tfar;
+    V3 sh_c;
+    uint32_t pixel, nv, flags, sample;
+    uint64_t rng_state;
+    float eta_scale, spread;
+    int medium;
+};
+
+struct RenderParams {
+    uint32_t spp_total;     // stream id = pixel * spp_total + sample
+    uint32_t sample_begin, sample_end;
+    uint64_t seed;
+    int width, height;
+};
+
+struct ShadeCounters { uint32_t bounces, shadow_rays, extend_rays, finished; };
+
+LJ_HD Pcg path_rng(const PathState &s, const RenderParams &rp) {
+    Pcg r;
+    r.state = s.rng_state;
+    r.inc = pcg_inc((uint64_t)s.pixel * rp.spp_total + s.sample);
+    return r;
+}
+
+// path_tracing.h:10-14 + state init (:44-53)
+LJ_HD void generate_path(const DevScene &sc, const RenderParams &rp, uint32_t pixel, uint32_t sample, PathState &s) {
+    Pcg rng = pcg_init((uint64_t)pixel * rp.spp_total + sample, rp.seed);
+    int x = pixel % rp.width, y = pixel / rp.width;
+    float u0 = pcg_uniform(rng), u1 = pcg_uniform(rng);
+    sample_primary_pixel(sc.camera, x, y, mk2(u0, u1), s.o, s.d);
+    s.tnear = 0;
+    s.tfar = LJ_INF;
+    s.T = mk3(1);
+    s.pdf_sa = -1;
+    s.L = mk3(0);
+    s.rr_prob = 1;
+    s.sh_tfar = -1;
+    s.sh_d = mk3(0);
+    s.sh_c = mk3(0);
+    s.pixel = pixel;
+    s.sample = sample;
+    s.nv = 1;
+    s.flags = kAlive | kOccupied;
+    s.rng_state = rng.state;
+    s.eta_scale = 1;
+    s.spread = init_ray_spread(rp.width, rp.height);
+    s.medium = sc.camera.medium_id;
+    s.hit.prim = kNoHit;
+    s.hit.t = 0; s.hit.u = 0; s.hit.v = 0;
+}
+
+LJ_HD float mis_power(float pa, float pb) { return (pa * pa) / (pa * pa + pb * pb); }
+
+// One shade step of the surface path tracer.  On return: s.flags has kAlive iff an extension ray
+// was written; s.sh_tfar >= 0 iff a shadow ray was written.
+LJ_HD void shade_path(const DevScene &sc, const RenderParams &rp, PathState &s, ShadeCounters &cnt) {
+    Pcg rng = path_rng(s, rp);
+    const bool primary = s.pdf_sa < 0;
+    s.sh_tfar = -1;
+    s.flags &= ~kAlive;
+
+    if (s.hit.prim == kNoHit) {
+        // path_tracing.h:17-28 (camera ray) / :284-307 (bsdf ray): environment map or nothing.
+        if (sc.envmap_light_id >= 0) {
+            const DevLight &env = sc.lights[sc.envmap_light_id];
+            PointAndNormal pn;
+            pn.position = mk3(0);
+            pn.normal = -s.d;
+            V3 Le = light_emission(sc, env, -s.d, s.spread, pn);
+            if (primary) {
+                s.L += Le;
+            } else {
+                float p2 = s.pdf_sa;  // G = 1
+                float p1 = light_pmf(sc, sc.envmap_light_id) * pdf_point_on_light(sc, env, pn, s.o);
+                s.L += s.T * Le * mis_power(p2, p1);
+            }
+        }
+        cnt.finished++;
+        return;
+    }
+
+    // intersect(): the camera ray carries the pixel's ray differential (path_tracing.h:14-16);
+    // bsdf rays are intersected with the default RayDifferential{} (:237), i.e. footprint 0.
+    Vertex vx = make_vertex(sc, s.o, s.d, s.hit, 0.f, primary ? s.spread : 0.f);
+    const DevShape &shape = sc.shapes[vx.shape_id];
+    V3 dir_view = -s.d;
+
+    if (shape.area_light_id >= 0) {
+        V3 Le = vertex_emission(sc, vx, dir_view);
+        if (primary) {
+            s.L += s.T * Le;  // :58-61
+        } else {
+            // :242-283 -- T already holds throughput * f / pdf_bsdf, so C2/p2 = T * Le
+            float G = fabsf(dot(s.d, vx.geometric_normal)) / distance_squared(vx.position, s.o);
+            float p2 = s.pdf_sa * G;
+            PointAndNormal lp;
+            lp.position = vx.position;
+            lp.normal = vx.geometric_normal;
+            float p1 = light_pmf(sc, shape.area_light_id) * pdf_point_on_light(sc, sc.lights[shape.area_light_id], lp, s.o);
+            s.L += s.T * Le * mis_power(p2, p1);
+        }
+    }
+    uint32_t nv = s.nv + 1;  // vertices on the path including vx
+    if (!primary) {
+        // :311-318 Russian roulette of the iteration that produced vx (its num_vertices == nv)
+        if ((int)nv - 1 >= sc.options.rr_depth) {
+            if (pcg_uniform(rng) > s.rr_prob) { cnt.finished++; s.rng_state = rng.state; return; }
+            s.T = s.T / s.rr_prob;
+        }
+    }
+    // loop condition of the next iteration (:66): num_vertices = nv + 1
+    if (!(sc.options.max_depth == -1 || (int)nv + 1 <= sc.options.max_depth + 1)) {
+        cnt.finished++; s.rng_state = rng.state; return;
+    }
+    cnt.bounces++;
+    if (vx.material_id < 0) { cnt.finished++; s.rng_state = rng.state; return; }  // reference asserts (:165)
+    const DevMaterial &mat = sc.materials[vx.material_id];
+
+    // ---- next event estimation, :94-207
+    float lu = pcg_uniform(rng), lv = pcg_uniform(rng);
+    float light_w = pcg_uniform(rng), shape_w = pcg_uniform(rng);
+    if (sc.num_lights > 0) {
+        int light_id = sample_light(sc, light_w);
+        const DevLight &light = sc.lights[light_id];
+        PointAndNormal pl = sample_point_on_light(sc, light, vx.position, mk2(lu, lv), shape_w);
+        V3 dir_light;
+        float G, tfar;
+        if (!light_is_envmap(light)) {
+            dir_light = normalize(pl.position - vx.position);
+            float dist = distance(pl.position, vx.position);
+            tfar = (1 - sc.shadow_eps) * dist;
+            G = fmaxf(-dot(dir_light, pl.normal), 0.f) / distance_squared(pl.position, vx.position);
+        } else {
+            dir_light = -pl.normal;
+            tfar = LJ_INF;
+            G = 1;
+        }
+        float p1 = light_pmf(sc, light_id) * pdf_point_on_light(sc, light, pl, vx.position);
+        if (G > 0 && p1 > 0) {
+            V3 f = bsdf_eval(sc, mat, dir_view, dir_light, vx, 0);
+            V3 Le = light_emission(sc, light, -dir_light, 0.f, pl);
+            float p2 = bsdf_pdf(sc, mat, dir_view, dir_light, vx) * G;
+            float w1 = mis_power(p1, p2);
+            V3 c = s.T * (f * Le) * (G / p1 * w1);
+            if (max3(c) > 0 || min3(c) < 0 || c.x != c.x || c.y != c.y || c.z != c.z) {
+                s.sh_d = dir_light;
+                s.sh_tfar = tfar;
+                s.sh_c = c;
+                cnt.shadow_rays++;
+            }
+        }
+    }
+
+    // ---- BSDF sampling, :209-259
+    float bu = pcg_uniform(rng), bv = pcg_uniform(rng), bw = pcg_uniform(rng);
+    s.rng_state = rng.state;
+    BsdfSample bs;
+    if (!bsdf_sample(sc, mat, dir_view, vx, mk2(bu, bv), bw, bs)) { cnt.finished++; return; }
+    // ray_diff.radius stays 0 for the whole path upstream (only .spread is updated, :227-230)
+    if (bs.eta == 0) {
+        s.spread = spread_reflect(0.f, s.spread, vx.mean_curvature, bs.roughness);
+    } else {
+        s.spread = spread_refract(0.f, s.spread, vx.mean_curvature, bs.eta, bs.roughness);
+        s.eta_scale /= (bs.eta * bs.eta);
+    }
+    V3 f = bsdf_eval(sc, mat, dir_view, bs.dir_out, vx, 0);
+    float p2 = bsdf_pdf(sc, mat, dir_view, bs.dir_out, vx);
+    if (!(p2 > 0)) { cnt.finished++; return; }
+    s.rr_prob = fminf(max3(s.T) / s.eta_scale, 0.95f);  // :313, evaluated with the pre-update throughput
+    s.T = s.T * f / p2;
+    s.pdf_sa = p2;
+    s.o = vx.position;
+    s.tnear = sc.isect_eps;
+    s.d = bs.dir_out;
+    s.tfar = LJ_INF;
+    s.nv = nv;
+    s.flags |= kAlive;
+    cnt.extend_rays++;
+}
+
+// ---- SoA load / store -------------------------------------------------------------------------
+LJ_HD void load_state(const PathPool &p, int i, PathState &s) {
+    V4 a = p.ray_o[i], b = p.ray_d[i], h = p.hit[i], t = p.thr[i], r = p.rad[i], m = p.meta[i], x = p.aux[i];
+    s.o = xyz(a); s.tnear = a.w;
+    s.d = xyz(b); s.tfar = b.w;
+    s.hit.t = h.x; s.hit.u = h.y; s.hit.v = h.z; s.hit.prim = (int)f2u(h.w);
+    s.T = xyz(t); s.pdf_sa = t.w;
+    s.L = xyz(r); s.rr_prob = r.w;
+    s.pixel = f2u(m.x);
+    uint32_t nf = f2u(m.y);
+    s.nv = nf & 0xffffu;
+    s.flags = nf & 0xffff0000u;
+    s.rng_state = (uint64_t)f2u(m.z) | ((uint64_t)f2u(m.w) << 32);
+    s.eta_scale = x.x; s.spread = x.y; s.sample = f2u(x.z); s.medium = (int)f2u(x.w);
+    s.sh_tfar = -1; s.sh_d = mk3(0); s.sh_c = mk3(0);
+}
+LJ_HD void store_state(const PathPool &p, int i, const PathState &s, bool store_ray) {
+    if (store_ray) {
+        p.ray_o[i] = mk4(s.o, s.tnear);
+        p.ray_d[i] = mk4(s.d, s.tfar);
+    }
+    p.thr[i] = mk4(s.T, s.pdf_sa);
+    p.rad[i] = mk4(s.L, s.rr_prob);
+    p.sh_d[i] = mk4(s.sh_d, s.sh_tfar);
+    if (s.sh_tfar >= 0) p.sh_c[i] = mk4(s.sh_c, 0.f);
+    p.meta[i] = mk4(u2f(s.pixel), u2f((s.nv & 0xffffu) | s.flags), u2f((uint32_t)s.rng_state), u2f((uint32_t)(s.rng_state >> 32)));
+    p.aux[i] = mk4(s.eta_scale, s.spread, u2f(s.sample), u2f((uint32_t)s.medium));
+}
+
+}  // namespace lj

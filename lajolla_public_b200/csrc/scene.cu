@@ -1,0 +1,502 @@
+// scene.cu -- lj_scene_create / destroy / introspection: flat description -> device tables.
+// Does what the reference's Scene::Scene does at scene.cpp:4-53 (commit geometry, scene bounds,
+// shape + light sampling tables, light power table) and make_mipmap (mipmap.h:24-48), for HBM.
+#include "scene.cuh"
+
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <chrono>
+
+namespace lj {
+
+static thread_local std::string g_error;
+void set_error(const std::string &msg) { g_error = msg; }
+int cuda_fail(cudaError_t e, const char *what) {
+    g_error = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
+    cudaGetLastError();
+    return LJ_ERR_CUDA;
+}
+
+namespace {
+
+// 2x2 box filter, mipmap.h:32-44.  One thread per destination texel.
+__global__ void k_mip_down3(const V4 *src, int sw, int sh, V4 *dst, int dw, int dh) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= dw * dh) return;
+    int x = i % dw, y = i / dw;
+    // A 1-texel-wide/high level makes upstream read past the image (mipmap.h:38-42 with
+    // prev.width == 1); the edge texel is replicated here instead.
+    int x1 = min(2 * x + 1, sw - 1), y1 = min(2 * y + 1, sh - 1);
+    V4 a = src[(2 * y) * sw + 2 * x], b = src[(2 * y) * sw + x1];
+    V4 c = src[y1 * sw + 2 * x], d = src[y1 * sw + x1];
+    dst[i] = mk4((a.x + b.x + c.x + d.x) / 4, (a.y + b.y + c.y + d.y) / 4, (a.z + b.z + c.z + d.z) / 4, 0.f);
+}
+__global__ void k_mip_down1(const float *src, int sw, int sh, float *dst, int dw, int dh) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= dw * dh) return;
+    int x = i % dw, y = i / dw;
+    int x1 = min(2 * x + 1, sw - 1), y1 = min(2 * y + 1, sh - 1);
+    dst[i] = (src[(2 * y) * sw + 2 * x] + src[(2 * y) * sw + x1] + src[y1 * sw + 2 * x] + src[y1 * sw + x1]) / 4;
+}
+
+struct Uploader {
+    lj_scene *s;
+    cudaError_t err = cudaSuccess;
+    template <typename T>
+    T *alloc(size_t n) {
+        void *p = nullptr;
+        size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) { if (err == cudaSuccess) err = e; return nullptr; }
+        s->allocations.push_back(p);
+        s->info.device_bytes += (int64_t)bytes;
+        return (T *)p;
+    }
+    template <typename T>
+    T *upload(const std::vector<T> &v) {
+        T *p = alloc<T>(v.size());
+        if (p && !v.empty()) {
+            cudaError_t e = cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+            if (e != cudaSuccess && err == cudaSuccess) err = e;
+        }
+        return p;
+    }
+};
+
+DevTexture conv_texture(const lj_texture_desc &t) {
+    DevTexture d;
+    memset(&d, 0, sizeof(d));
+    d.kind = t.kind;
+    d.image_id = t.image_id;
+    for (int c = 0; c < 3; c++) { d.v0[c] = t.value[c]; d.v1[c] = t.color1[c]; }
+    d.uscale = t.uscale; d.vscale = t.vscale; d.uoffset = t.uoffset; d.voffset = t.voffset;
+    return d;
+}
+
+double lum(const float *c) { return c[0] * 0.212671 + c[1] * 0.715160 + c[2] * 0.072169; }
+
+DevVolume conv_volume(const lj_volume_desc &v, Uploader &up) {
+    DevVolume d;
+    memset(&d, 0, sizeof(d));
+    d.is_grid = v.is_grid;
+    for (int c = 0; c < 3; c++) {
+        d.res[c] = v.res[c]; d.value[c] = v.value[c]; d.p_min[c] = v.p_min[c]; d.p_max[c] = v.p_max[c];
+        d.max_data[c] = v.value[c];
+    }
+    d.scale = v.scale;
+    if (v.is_grid) {
+        size_t n = (size_t)v.res[0] * v.res[1] * v.res[2];
+        std::vector<V4> tex(n);
+        float mx[3] = {0, 0, 0};  // volume.h get_max_value starts from the first voxel; data are >= 0 in practice
+        for (size_t i = 0; i < n; i++) {
+            tex[i] = mk4(v.data[3 * i], v.data[3 * i + 1], v.data[3 * i + 2], 0.f);
+            for (int c = 0; c < 3; c++) mx[c] = i == 0 ? v.data[c] : std::max(mx[c], v.data[3 * i + c]);
+        }
+        for (int c = 0; c < 3; c++) d.max_data[c] = mx[c];
+        d.data = up.upload(tex);
+    }
+    return d;
+}
+
+}  // namespace
+}  // namespace lj
+
+using namespace lj;
+
+extern "C" const char *lj_last_error(void) { return g_error.c_str(); }
+
+extern "C" int lj_init(int device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device visible: libljb200 has no CPU path");
+        return LJ_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= count) { set_error("device index out of range"); return LJ_ERR_INVALID; }
+    LJ_CUDA(cudaSetDevice(device));
+    LJ_CUDA(cudaFree(0));
+    return LJ_OK;
+}
+
+extern "C" void lj_scene_destroy(lj_scene *s) {
+    if (!s) return;
+    for (void *p : s->allocations) cudaFree(p);
+    if (s->pool_block) cudaFree(s->pool_block);
+    if (s->d_film) cudaFree(s->d_film);
+    if (s->d_film_sq) cudaFree(s->d_film_sq);
+    for (auto &e : s->ev) if (e) cudaEventDestroy(e);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+extern "C" int lj_scene_create(const lj_scene_desc *desc, lj_scene **out) {
+    if (!desc || !out) { set_error("null argument"); return LJ_ERR_INVALID; }
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device visible: libljb200 has no CPU path");
+        return LJ_ERR_NO_DEVICE;
+    }
+    if (desc->num_shapes <= 0) { set_error("scene has no shapes"); return LJ_ERR_INVALID; }
+    auto t_start = std::chrono::steady_clock::now();
+    lj_scene *s = new lj_scene();
+    memset(&s->info, 0, sizeof(s->info));
+    memset(&s->dev, 0, sizeof(s->dev));
+    memset(&s->pool, 0, sizeof(s->pool));
+    cudaGetDevice(&s->device);
+    Uploader up{s};
+    DevScene &sc = s->dev;
+    auto fail = [&](int code, const std::string &msg) { set_error(msg); lj_scene_destroy(s); return code; };
+
+    // ---- camera / options
+    memcpy(sc.camera.cam_to_world.m, desc->camera.cam_to_world, 64);
+    memcpy(sc.camera.sample_to_cam.m, desc->camera.sample_to_cam, 64);
+    sc.camera.width = desc->camera.width;
+    sc.camera.height = desc->camera.height;
+    sc.camera.filter_type = desc->camera.filter_type;
+    sc.camera.filter_param = desc->camera.filter_param;
+    sc.camera.medium_id = desc->camera.medium_id;
+    sc.options.integrator = desc->options.integrator;
+    sc.options.spp = desc->options.samples_per_pixel;
+    sc.options.max_depth = desc->options.max_depth;
+    sc.options.rr_depth = desc->options.rr_depth;
+    sc.options.vol_path_version = desc->options.vol_path_version;
+    sc.options.max_null_collisions = desc->options.max_null_collisions;
+    if (sc.camera.width <= 0 || sc.camera.height <= 0) return fail(LJ_ERR_INVALID, "bad film size");
+
+    // ---- geometry pools
+    std::vector<float> positions, normals, uvs, tri_cdf;
+    std::vector<int> indices, prim_shape, prim_local;
+    std::vector<DevShape> shapes(desc->num_shapes);
+    int n_tris = 0, n_spheres = 0;
+    for (int i = 0; i < desc->num_shapes; i++) {
+        const lj_shape_desc &sd = desc->shapes[i];
+        DevShape &sh = shapes[i];
+        memset(&sh, 0, sizeof(sh));
+        sh.type = sd.type;
+        sh.material_id = sd.material_id;
+        sh.area_light_id = sd.area_light_id;
+        sh.interior_medium_id = sd.interior_medium_id;
+        sh.exterior_medium_id = sd.exterior_medium_id;
+        if (sd.material_id >= desc->num_materials) return fail(LJ_ERR_INVALID, "shape material_id out of range");
+        if (sd.type == LJ_SHAPE_SPHERE) {
+            sh.cx = sd.center[0]; sh.cy = sd.center[1]; sh.cz = sd.center[2];
+            sh.radius = sd.radius;
+            prim_shape.push_back(i);
+            prim_local.push_back(0);
+            n_spheres++;
+            continue;
+        }
+        if (sd.type != LJ_SHAPE_MESH || !sd.positions || !sd.indices || sd.num_vertices <= 0 || sd.num_triangles < 0)
+            return fail(LJ_ERR_INVALID, "malformed mesh shape");
+        int vbase = (int)(positions.size() / 3);
+        sh.vertex_offset = vbase;
+        sh.tri_offset = (int)(indices.size() / 3);
+        sh.num_tris = sd.num_triangles;
+        sh.has_normals = sd.normals != nullptr;
+        sh.has_uvs = sd.uvs != nullptr;
+        positions.insert(positions.end(), sd.positions, sd.positions + 3 * (size_t)sd.num_vertices);
+        if (sd.normals) normals.insert(normals.end(), sd.normals, sd.normals + 3 * (size_t)sd.num_vertices);
+        else normals.resize(normals.size() + 3 * (size_t)sd.num_vertices, 0.f);
+        if (sd.uvs) uvs.insert(uvs.end(), sd.uvs, sd.uvs + 2 * (size_t)sd.num_vertices);
+        else uvs.resize(uvs.size() + 2 * (size_t)sd.num_vertices, 0.f);
+        // triangle areas -> TableDist1D, triangle_mesh.inl:60-75 + table_dist.cpp:3-25 (double, then fp32)
+        std::vector<double> cdf(sd.num_triangles + 1, 0.0);
+        for (int t = 0; t < sd.num_triangles; t++) {
+            int i0 = sd.indices[3 * t], i1 = sd.indices[3 * t + 1], i2 = sd.indices[3 * t + 2];
+            if (i0 < 0 || i1 < 0 || i2 < 0 || i0 >= sd.num_vertices || i1 >= sd.num_vertices || i2 >= sd.num_vertices)
+                return fail(LJ_ERR_INVALID, "mesh index out of range");
+            indices.push_back(vbase + i0); indices.push_back(vbase + i1); indices.push_back(vbase + i2);
+            const float *p0 = sd.positions + 3 * i0, *p1 = sd.positions + 3 * i1, *p2 = sd.positions + 3 * i2;
+            double e1[3], e2[3];
+            for (int c = 0; c < 3; c++) { e1[c] = (double)p1[c] - p0[c]; e2[c] = (double)p2[c] - p0[c]; }
+            double cx = e1[1] * e2[2] - e1[2] * e2[1], cy = e1[2] * e2[0] - e1[0] * e2[2], cz = e1[0] * e2[1] - e1[1] * e2[0];
+            cdf[t + 1] = cdf[t] + sqrt(cx * cx + cy * cy + cz * cz) / 2;
+            prim_shape.push_back(i);
+            prim_local.push_back(t);
+        }
+        double total = cdf[sd.num_triangles];
+        sh.total_area = (float)total;
+        sh.cdf_offset = (int)tri_cdf.size();
+        if (sd.area_light_id >= 0) {  // the table is only ever sampled for emitters
+            for (int t = 0; t <= sd.num_triangles; t++) {
+                double v = total > 0 ? cdf[t] / total : (double)t / std::max(sd.num_triangles, 1);
+                tri_cdf.push_back((float)v);
+            }
+            tri_cdf.back() = 1.f;  // upstream leaves cdf[n] un-normalised (TRAP a18); same samples either way
+        }
+        n_tris += sd.num_triangles;
+    }
+    int n_prims = (int)prim_shape.size();
+    if (n_prims == 0) return fail(LJ_ERR_INVALID, "scene has no primitives");
+    sc.positions = up.upload(positions);
+    sc.normals = up.upload(normals);
+    sc.uvs = up.upload(uvs);
+    sc.indices = up.upload(indices);
+    sc.tri_cdf = up.upload(tri_cdf);
+    sc.shapes = up.upload(shapes);
+    sc.num_shapes = desc->num_shapes;
+    int *d_prim_shape = up.upload(prim_shape);
+    int *d_prim_local = up.upload(prim_local);
+    if (up.err != cudaSuccess) { int r = cuda_fail(up.err, "geometry upload"); lj_scene_destroy(s); return r; }
+
+    cudaStreamCreate(&s->stream);
+    for (auto &e : s->ev) cudaEventCreate(&e);
+
+    // ---- images + mip chains (mipmap.h:24-48) built on the device
+    std::vector<DevImage> images(std::max(desc->num_images, 0));
+    size_t total1 = 0, total3 = 0;
+    for (int i = 0; i < desc->num_images; i++) {
+        const lj_image_desc &im = desc->images[i];
+        if (im.width <= 0 || im.height <= 0 || (im.channels != 1 && im.channels != 3) || !im.data)
+            return fail(LJ_ERR_INVALID, "malformed image");
+        DevImage &d = images[i];
+        memset(&d, 0, sizeof(d));
+        d.channels = im.channels;
+        int size = std::max(im.width, im.height);
+        d.levels = std::min((int)ceil(log2((double)size) + 1), kMaxMipLevels);
+        int w = im.width, h = im.height;
+        size_t &total = im.channels == 3 ? total3 : total1;
+        for (int l = 0; l < d.levels; l++) {
+            d.w[l] = w; d.h[l] = h; d.offset[l] = (int)total;
+            total += (size_t)w * h;
+            w = std::max(w / 2, 1); h = std::max(h / 2, 1);
+        }
+    }
+    V4 *texels3 = up.alloc<V4>(total3);
+    float *texels1 = up.alloc<float>(total1);
+    if (up.err != cudaSuccess) { int r = cuda_fail(up.err, "texture alloc"); lj_scene_destroy(s); return r; }
+    auto t_prep0 = std::chrono::steady_clock::now();
+    for (int i = 0; i < desc->num_images; i++) {
+        const lj_image_desc &im = desc->images[i];
+        const DevImage &d = images[i];
+        size_t n0 = (size_t)im.width * im.height;
+        if (im.channels == 3) {
+            std::vector<V4> l0(n0);
+            for (size_t k = 0; k < n0; k++) l0[k] = mk4(im.data[3 * k], im.data[3 * k + 1], im.data[3 * k + 2], 0.f);
+            cudaMemcpyAsync(texels3 + d.offset[0], l0.data(), n0 * sizeof(V4), cudaMemcpyHostToDevice, s->stream);
+            cudaStreamSynchronize(s->stream);
+            for (int l = 1; l < d.levels; l++) {
+                int n = d.w[l] * d.h[l];
+                LJ_LAUNCH(k_mip_down3, (n + 255) / 256, 256, s->stream, texels3 + d.offset[l - 1], d.w[l - 1], d.h[l - 1], texels3 + d.offset[l], d.w[l], d.h[l]);
+            }
+        } else {
+            cudaMemcpyAsync(texels1 + d.offset[0], im.data, n0 * sizeof(float), cudaMemcpyHostToDevice, s->stream);
+            for (int l = 1; l < d.levels; l++) {
+                int n = d.w[l] * d.h[l];
+                LJ_LAUNCH(k_mip_down1, (n + 255) / 256, 256, s->stream, texels1 + d.offset[l - 1], d.w[l - 1], d.h[l - 1], texels1 + d.offset[l], d.w[l], d.h[l]);
+            }
+        }
+    }
+    {
+        cudaError_t e = cudaStreamSynchronize(s->stream);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) { int r = cuda_fail(e, "mip build"); lj_scene_destroy(s); return r; }
+    }
+    s->h_images3 = images;
+    sc.images1 = sc.images3 = up.upload(images);
+    sc.texels1 = texels1;
+    sc.texels3 = texels3;
+
+    // ---- materials
+    std::vector<DevMaterial> mats(std::max(desc->num_materials, 0));
+    for (int i = 0; i < desc->num_materials; i++) {
+        const lj_material_desc &md = desc->materials[i];
+        DevMaterial &m = mats[i];
+        memset(&m, 0, sizeof(m));
+        m.type = md.type;
+        m.eta = md.eta;
+        if (md.type < 0 || md.type > LJ_MAT_DISNEY_BSDF) return fail(LJ_ERR_INVALID, "unknown material type");
+        for (int k = 0; k < LJ_NUM_TEX_SLOTS; k++) {
+            m.tex[k] = conv_texture(md.tex[k]);
+            if (md.tex[k].kind == LJ_TEX_IMAGE && (md.tex[k].image_id < 0 || md.tex[k].image_id >= desc->num_images))
+                return fail(LJ_ERR_INVALID, "texture image_id out of range");
+        }
+    }
+    sc.materials = up.upload(mats);
+    sc.num_materials = desc->num_materials;
+
+    // ---- BVH (K0)
+    BvhResult bvh;
+    auto t_bvh0 = std::chrono::steady_clock::now();
+    {
+        cudaError_t e = build_bvh2(sc, d_prim_shape, d_prim_local, n_prims, s->stream, &bvh);
+        if (e != cudaSuccess) { int r = cuda_fail(e, "BVH build"); lj_scene_destroy(s); return r; }
+    }
+    auto t_bvh1 = std::chrono::steady_clock::now();
+    s->allocations.push_back(bvh.nodes);
+    s->allocations.push_back(bvh.prims);
+    s->info.device_bytes += (int64_t)bvh.num_nodes * sizeof(DevNode2) + (int64_t)n_prims * sizeof(DevPrim);
+    sc.nodes2 = bvh.nodes;
+    sc.prims = bvh.prims;
+    sc.num_prims = n_prims;
+
+    // ---- scene bounds -> bounding sphere + epsilons (scene.cpp:29-34, scene.h:99-105)
+    {
+        double d2 = 0;
+        for (int c = 0; c < 3; c++) {
+            double lo = (&bvh.bounds.lo.x)[c], hi = (&bvh.bounds.hi.x)[c];
+            d2 += (hi - lo) * (hi - lo);
+            (&sc.bsphere_center.x)[c] = (float)((lo + hi) / 2);
+            s->info.bounds_lo[c] = (float)lo;
+            s->info.bounds_hi[c] = (float)hi;
+            s->info.bsphere_center[c] = (float)((lo + hi) / 2);
+        }
+        double radius = sqrt(d2) / 2;
+        sc.bsphere_radius = (float)radius;
+        sc.shadow_eps = sc.isect_eps = (float)std::min(radius * 1e-5, 0.01);
+        s->info.bsphere_radius = sc.bsphere_radius;
+        s->info.shadow_epsilon = sc.shadow_eps;
+    }
+
+    // ---- lights: envmap table (envmap.inl:75-98, table_dist.cpp:40-115), power table (scene.cpp:48-52)
+    std::vector<DevLight> lights(std::max(desc->num_lights, 0));
+    std::vector<double> power(lights.size(), 0.0);
+    sc.envmap_light_id = desc->envmap_light_id;
+    for (int i = 0; i < desc->num_lights; i++) {
+        const lj_light_desc &ld = desc->lights[i];
+        DevLight &l = lights[i];
+        memset(&l, 0, sizeof(l));
+        l.type = ld.type;
+        l.shape_id = ld.shape_id;
+        for (int c = 0; c < 3; c++) l.intensity[c] = ld.intensity[c];
+        if (ld.type == LJ_LIGHT_AREA) {
+            if (ld.shape_id < 0 || ld.shape_id >= desc->num_shapes) return fail(LJ_ERR_INVALID, "light shape_id out of range");
+            const DevShape &sh = shapes[ld.shape_id];
+            double area = sh.type == 0 ? 4 * M_PI * (double)sh.radius * sh.radius : (double)sh.total_area;
+            power[i] = lum(ld.intensity) * area * M_PI;  // diffuse_area_light.inl:1-3
+            continue;
+        }
+        l.values = conv_texture(ld.values);
+        memcpy(l.to_world.m, ld.to_world, 64);
+        memcpy(l.to_local.m, ld.to_local, 64);
+        l.scale = ld.scale;
+        if (ld.values.kind != LJ_TEX_IMAGE) { power[i] = 0; continue; }  // envmap.inl:76: only image envmaps get a table
+        if (ld.values.image_id < 0 || ld.values.image_id >= desc->num_images || desc->images[ld.values.image_id].channels != 3)
+            return fail(LJ_ERR_INVALID, "envmap image invalid");
+        const lj_image_desc &im = desc->images[ld.values.image_id];
+        int w = im.width, h = im.height;
+        std::vector<double> f((size_t)w * h);
+        for (int y = 0; y < h; y++) {
+            double sin_el = sin(M_PI * (y + 0.5) / h);
+            for (int x = 0; x < w; x++) f[(size_t)y * w + x] = lum(im.data + 3 * ((size_t)y * w + x)) * sin_el;
+        }
+        std::vector<float> cdf_rows((size_t)h * (w + 1)), pdf_rows((size_t)h * w), cdf_m(h + 1), pdf_m(h);
+        std::vector<double> row_int(h);
+        for (int y = 0; y < h; y++) {
+            std::vector<double> c(w + 1, 0.0);
+            for (int x = 0; x < w; x++) c[x + 1] = c[x] + f[(size_t)y * w + x];
+            double integral = c[w];
+            row_int[y] = integral;
+            for (int x = 0; x < w; x++) {
+                cdf_rows[(size_t)y * (w + 1) + x] = (float)(integral > 0 ? c[x] / integral : (double)x / w);
+                pdf_rows[(size_t)y * w + x] = (float)(integral > 0 ? f[(size_t)y * w + x] / integral : 1.0 / w);
+            }
+            cdf_rows[(size_t)y * (w + 1) + w] = 1.f;
+        }
+        std::vector<double> cm(h + 1, 0.0);
+        for (int y = 0; y < h; y++) cm[y + 1] = cm[y] + row_int[y];
+        double total_values = cm[h];
+        for (int y = 0; y < h; y++) {
+            cdf_m[y] = (float)(total_values > 0 ? cm[y] / total_values : (double)y / h);
+            pdf_m[y] = (float)(total_values > 0 ? row_int[y] / total_values : 1.0 / h);
+        }
+        cdf_m[h] = 1.f;
+        sc.envmap_dist.width = w;
+        sc.envmap_dist.height = h;
+        sc.envmap_dist.total_values = (float)total_values;
+        sc.envmap_dist.cdf_rows = up.upload(cdf_rows);
+        sc.envmap_dist.pdf_rows = up.upload(pdf_rows);
+        sc.envmap_dist.cdf_marginals = up.upload(cdf_m);
+        sc.envmap_dist.pdf_marginals = up.upload(pdf_m);
+        double R = sc.bsphere_radius;
+        power[i] = M_PI * R * R * total_values / ((double)w * h);  // envmap.inl:1-5
+    }
+    {
+        int n = (int)lights.size();
+        s->h_light_pmf.assign(n, 0.f);
+        s->h_light_cdf.assign(n + 1, 0.f);
+        std::vector<double> cdf(n + 1, 0.0);
+        for (int i = 0; i < n; i++) cdf[i + 1] = cdf[i] + power[i];
+        double total = n ? cdf[n] : 0;
+        for (int i = 0; i < n; i++) {
+            s->h_light_pmf[i] = (float)(total > 0 ? power[i] / total : 1.0 / n);
+            s->h_light_cdf[i] = (float)(total > 0 ? cdf[i] / total : (double)i / n);
+        }
+        s->h_light_cdf[n] = 1.f;
+    }
+    sc.lights = up.upload(lights);
+    sc.num_lights = desc->num_lights;
+    sc.light_pmf = up.upload(s->h_light_pmf);
+    sc.light_cdf = up.upload(s->h_light_cdf);
+
+    // ---- media
+    std::vector<DevMedium> media(std::max(desc->num_media, 0));
+    for (int i = 0; i < desc->num_media; i++) {
+        const lj_medium_desc &md = desc->media[i];
+        DevMedium &m = media[i];
+        memset(&m, 0, sizeof(m));
+        m.type = md.type;
+        m.phase_type = md.phase_type;
+        m.phase_g = md.phase_g;
+        for (int c = 0; c < 3; c++) { m.sigma_a[c] = md.sigma_a[c]; m.sigma_s[c] = md.sigma_s[c]; }
+        if (md.type == LJ_MEDIUM_HETEROGENEOUS) {
+            m.albedo = conv_volume(md.albedo, up);
+            m.density = conv_volume(md.density, up);
+        }
+    }
+    sc.media = up.upload(media);
+    sc.num_media = desc->num_media;
+    if (up.err != cudaSuccess) { int r = cuda_fail(up.err, "table upload"); lj_scene_destroy(s); return r; }
+    cudaDeviceSynchronize();
+
+    auto t_end = std::chrono::steady_clock::now();
+    auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    s->info.num_prims = n_prims;
+    s->info.num_triangles = n_tris;
+    s->info.num_spheres = n_spheres;
+    s->info.num_bvh_nodes = bvh.num_nodes;
+    s->info.bvh_width = 2;
+    s->info.bvh_build_ms = ms(t_bvh0, t_bvh1);
+    s->info.prep_ms = ms(t_prep0, t_bvh0);
+    s->info.upload_ms = ms(t_start, t_end) - s->info.bvh_build_ms - s->info.prep_ms;
+    s->info.sah_cost = bvh.sah_cost;
+    *out = s;
+    return LJ_OK;
+}
+
+extern "C" int lj_scene_get_info(lj_scene *s, lj_scene_info *info) {
+    if (!s || !info) { set_error("null argument"); return LJ_ERR_INVALID; }
+    *info = s->info;
+    return LJ_OK;
+}
+
+extern "C" int lj_scene_get_light_table(lj_scene *s, float *pmf, float *cdf) {
+    if (!s) { set_error("null argument"); return LJ_ERR_INVALID; }
+    if (pmf) memcpy(pmf, s->h_light_pmf.data(), s->h_light_pmf.size() * sizeof(float));
+    if (cdf) memcpy(cdf, s->h_light_cdf.data(), s->h_light_cdf.size() * sizeof(float));
+    return LJ_OK;
+}
+
+extern "C" int lj_scene_get_mip_level(lj_scene *s, int32_t channels, int32_t image_id, int32_t level,
+                                      int32_t *width, int32_t *height, float *data) {
+    if (!s || image_id < 0 || image_id >= (int)s->h_images3.size()) { set_error("bad image id"); return LJ_ERR_INVALID; }
+    const DevImage &d = s->h_images3[image_id];
+    if (d.channels != channels || level < 0 || level >= d.levels) { set_error("bad level/channels"); return LJ_ERR_INVALID; }
+    if (width) *width = d.w[level];
+    if (height) *height = d.h[level];
+    if (!data) return LJ_OK;
+    size_t n = (size_t)d.w[level] * d.h[level];
+    if (channels == 1) {
+        LJ_CUDA(cudaMemcpy(data, s->dev.texels1 + d.offset[level], n * sizeof(float), cudaMemcpyDeviceToHost));
+    } else {
+        std::vector<V4> tmp(n);
+        LJ_CUDA(cudaMemcpy(tmp.data(), s->dev.texels3 + d.offset[level], n * sizeof(V4), cudaMemcpyDeviceToHost));
+        for (size_t k = 0; k < n; k++) { data[3 * k] = tmp[k].x; data[3 * k + 1] = tmp[k].y; data[3 * k + 2] = tmp[k].z; }
+    }
+    return LJ_OK;
+}

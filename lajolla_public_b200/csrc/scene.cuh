@@ -1,0 +1,39 @@
+// scene.cuh -- the opaque lj_scene: device allocations + the DevScene handed to every kernel.
+#pragma once
+#include "lj_cuda.h"
+
+#include <string>
+#include <vector>
+
+#include "../../include/lajolla_b200.h"
+#include "bvh_build.cuh"
+#include "lj_path.h"
+
+struct lj_scene {
+    lj::DevScene dev;                 // by-value kernel parameter
+    std::vector<void *> allocations;  // everything cudaMalloc'ed for this scene
+    lj_scene_info info;
+    int device = 0;
+    // host copies needed by introspection entry points
+    std::vector<float> h_light_pmf, h_light_cdf;
+    std::vector<lj::DevImage> h_images1, h_images3;
+    // persistent path pool (allocated on first render, reused)
+    lj::PathPool pool;
+    void *pool_block = nullptr;
+    int pool_capacity = 0;
+    float *d_film = nullptr;    // w*h*4 fp32: sum rgb, sample count
+    float *d_film_sq = nullptr; // w*h*4 fp32: sum of squares rgb
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8] = {};
+};
+
+namespace lj {
+void set_error(const std::string &msg);
+int cuda_fail(cudaError_t e, const char *what);
+}  // namespace lj
+
+#define LJ_CUDA(x)                                                        \
+    do {                                                                  \
+        cudaError_t e__ = (x);                                            \
+        if (e__ != cudaSuccess) return lj::cuda_fail(e__, #x);            \
+    } while (0)

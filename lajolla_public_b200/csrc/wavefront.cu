@@ -1,0 +1,350 @@
+// wavefront.cu -- the wavefront path tracer: regenerate / extend / shade / shadow kernels over a
+// pool of path records resident in HBM, and the render entry points of the C ABI.
+// Replaces the reference's tile thread pool (render.cpp:71-152, parallel.cpp) and the per-sample
+// control flow of path_tracing.h.  Stage kernels:
+//   k_regen   K1+K7  flush finished paths to the film, start new camera paths in free slots
+//   k_extend  K2     closest-hit traversal for every live path
+//   k_shade   K4     emission+MIS, Russian roulette, NEE sample, BSDF sample (lj_path.h)
+//   k_shadow  K3     any-hit traversal of the NEE shadow rays, adds unoccluded contributions
+#include "scene.cuh"
+
+#include <vector>
+
+namespace lj {
+
+enum { C_SAMPLES = 0, C_CLOSEST, C_SHADOW, C_BOUNCES, C_ACTIVE, C_NEXT, C_COUNT };
+
+struct WaveArgs {
+    PathPool pool;
+    RenderParams rp;
+    unsigned long long *counters;  // C_COUNT
+    float *film;                   // w*h*4: sum rgb, n
+    float *film_sq;                // w*h*4: sum of squares rgb (may be null)
+    unsigned long long total_items;  // padded pixels * samples in this call
+    int tiles_x, tiles_y;
+};
+
+__device__ __forceinline__ void warp_add(unsigned long long *ctr, unsigned v) {
+    unsigned s = __reduce_add_sync(0xffffffffu, v);
+    if (LJ_LANE() == 0 && s) atomicAdd(ctr, (unsigned long long)s);
+}
+
+// K1 + K7.  Work item k -> (sample, 8x4 pixel tile, lane) so one warp starts 32 neighbouring pixels.
+__global__ void __launch_bounds__(256) k_regen(const LJ_GRID_CONSTANT DevScene sc, const LJ_GRID_CONSTANT WaveArgs a) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool in_range = i < a.pool.capacity;
+    uint32_t flags = 0, pixel = 0;
+    V4 meta = mk4(0, 0, 0, 0);
+    if (in_range) {
+        meta = a.pool.meta[i];
+        flags = f2u(meta.y) & 0xffff0000u;
+        pixel = f2u(meta.x);
+    }
+    bool alive = in_range && (flags & kAlive);
+    bool need = in_range && !alive;
+    unsigned finished = 0;
+    if (need && (flags & kOccupied)) {
+        // K7: accumulate the finished sample (render.cpp:92) -- non-finite samples are dropped
+        V4 r = a.pool.rad[i];
+        if (is_finite(r.x) && is_finite(r.y) && is_finite(r.z)) {
+            float *px = a.film + 4 * (size_t)pixel;
+            atomicAdd(px + 0, r.x); atomicAdd(px + 1, r.y); atomicAdd(px + 2, r.z); atomicAdd(px + 3, 1.f);
+            if (a.film_sq) {
+                float *sq = a.film_sq + 4 * (size_t)pixel;
+                atomicAdd(sq + 0, r.x * r.x); atomicAdd(sq + 1, r.y * r.y); atomicAdd(sq + 2, r.z * r.z);
+            }
+        }
+        finished = 1;
+    }
+    // warp-aggregated grab of the next work items
+    unsigned mask = __ballot_sync(0xffffffffu, need);
+    unsigned long long base = 0;
+    int lane = LJ_LANE();
+    if (mask) {
+        int leader = __ffs(mask) - 1;
+        if (lane == leader) base = atomicAdd(&a.counters[C_NEXT], (unsigned long long)__popc(mask));
+        base = __shfl_sync(0xffffffffu, base, leader);
+    }
+    unsigned started = 0;
+    if (need) {
+        unsigned long long k = base + __popc(mask & ((1u << lane) - 1));
+        bool ok = k < a.total_items;
+        uint32_t x = 0, y = 0, sample = 0;
+        if (ok) {
+            unsigned long long per_sample = (unsigned long long)a.tiles_x * a.tiles_y * 32ull;
+            sample = a.rp.sample_begin + (uint32_t)(k / per_sample);
+            uint32_t p = (uint32_t)(k % per_sample);
+            uint32_t tile = p >> 5, l = p & 31;
+            x = (tile % a.tiles_x) * 8 + (l & 7);
+            y = (tile / a.tiles_x) * 4 + (l >> 3);
+            ok = x < (uint32_t)a.rp.width && y < (uint32_t)a.rp.height;
+        }
+        if (ok) {
+            PathState s;
+            generate_path(sc, a.rp, y * a.rp.width + x, sample, s);
+            store_state(a.pool, i, s, true);
+            a.pool.hit[i] = mk4(0, 0, 0, u2f((uint32_t)kNoHit));
+            started = 1;
+        } else if (flags) {
+            a.pool.meta[i] = mk4(meta.x, u2f(0u), meta.z, meta.w);  // slot is now empty
+            a.pool.sh_d[i] = mk4(0, 0, 0, -1.f);
+        }
+    }
+    warp_add(&a.counters[C_SAMPLES], finished);
+    warp_add(&a.counters[C_ACTIVE], started + (alive ? 1u : 0u));
+}
+
+// K2
+__global__ void __launch_bounds__(256) k_extend(const LJ_GRID_CONSTANT DevScene sc, const LJ_GRID_CONSTANT WaveArgs a) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool active = false;
+    if (i < a.pool.capacity) {
+        uint32_t flags = f2u(a.pool.meta[i].y);
+        active = flags & kAlive;
+        if (active) {
+            V4 o = a.pool.ray_o[i], d = a.pool.ray_d[i];
+            Hit h;
+            trace2<false>(sc.nodes2, sc.prims, xyz(o), xyz(d), o.w, d.w, h);
+            a.pool.hit[i] = mk4(h.t, h.u, h.v, u2f((uint32_t)h.prim));
+        }
+    }
+    warp_add(&a.counters[C_CLOSEST], active ? 1u : 0u);
+}
+
+// K4
+__global__ void __launch_bounds__(128) k_shade(const LJ_GRID_CONSTANT DevScene sc, const LJ_GRID_CONSTANT WaveArgs a) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    ShadeCounters cnt = {0, 0, 0, 0};
+    if (i < a.pool.capacity) {
+        uint32_t flags = f2u(a.pool.meta[i].y);
+        if (flags & kAlive) {
+            PathState s;
+            load_state(a.pool, i, s);
+            shade_path(sc, a.rp, s, cnt);
+            store_state(a.pool, i, s, (s.flags & kAlive) != 0);
+        }
+    }
+    warp_add(&a.counters[C_BOUNCES], cnt.bounces);
+}
+
+// K3
+__global__ void __launch_bounds__(256) k_shadow(const LJ_GRID_CONSTANT DevScene sc, const LJ_GRID_CONSTANT WaveArgs a) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool active = false;
+    if (i < a.pool.capacity) {
+        V4 sd = a.pool.sh_d[i];
+        active = sd.w >= 0;
+        if (active) {
+            V4 o = a.pool.ray_o[i];
+            // The shadow ray starts at the shaded vertex.  If the path continued, ray_o holds that
+            // vertex (the extension ray starts there too); if it ended, ray_o was not overwritten
+            // and still holds the previous origin, so the vertex is rebuilt from the old ray + hit.
+            uint32_t flags = f2u(a.pool.meta[i].y);
+            V3 org = xyz(o);
+            if (!(flags & kAlive)) org = xyz(o) + xyz(a.pool.ray_d[i]) * a.pool.hit[i].x;
+            Hit h;
+            bool occ = trace2<true>(sc.nodes2, sc.prims, org, xyz(sd), sc.shadow_eps, sd.w, h);
+            if (!occ) {
+                V4 r = a.pool.rad[i], c = a.pool.sh_c[i];
+                a.pool.rad[i] = mk4(r.x + c.x, r.y + c.y, r.z + c.z, r.w);
+            }
+            a.pool.sh_d[i] = mk4(sd.x, sd.y, sd.z, -1.f);
+        }
+    }
+    warp_add(&a.counters[C_SHADOW], active ? 1u : 0u);
+}
+
+__global__ void k_clear_pool(PathPool pool) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= pool.capacity) return;
+    pool.meta[i] = mk4(0, 0, 0, 0);
+    pool.sh_d[i] = mk4(0, 0, 0, -1.f);
+    pool.rad[i] = mk4(0, 0, 0, 1.f);
+}
+
+// film -> caller's w*h*3 buffer (render.cpp:94 divides by spp) and optional variance of the mean
+__global__ void k_resolve(const float *film, const float *film_sq, int npix, float inv_n, int normalize, float *out, float *var_out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    float4 f = reinterpret_cast<const float4 *>(film)[i];
+    float s = normalize ? inv_n : 1.f;
+    out[3 * i] = f.x * s; out[3 * i + 1] = f.y * s; out[3 * i + 2] = f.z * s;
+    if (var_out && film_sq) {
+        float4 q = reinterpret_cast<const float4 *>(film_sq)[i];
+        float n = f.w;
+        float v[3] = {0, 0, 0};
+        if (n > 1) {
+            v[0] = fmaxf(q.x - f.x * f.x / n, 0.f) / (n - 1) / n;
+            v[1] = fmaxf(q.y - f.y * f.y / n, 0.f) / (n - 1) / n;
+            v[2] = fmaxf(q.z - f.z * f.z / n, 0.f) / (n - 1) / n;
+        }
+        var_out[3 * i] = v[0]; var_out[3 * i + 1] = v[1]; var_out[3 * i + 2] = v[2];
+    }
+}
+
+static int ensure_pool(lj_scene *s, int capacity) {
+    if (s->pool_capacity == capacity && s->pool_block) return LJ_OK;
+    if (s->pool_block) { cudaFree(s->pool_block); s->pool_block = nullptr; }
+    const int kFields = 9;
+    LJ_CUDA(cudaMalloc(&s->pool_block, (size_t)capacity * sizeof(V4) * kFields));
+    V4 *base = (V4 *)s->pool_block;
+    PathPool &p = s->pool;
+    p.ray_o = base + (size_t)capacity * 0; p.ray_d = base + (size_t)capacity * 1; p.hit = base + (size_t)capacity * 2;
+    p.thr = base + (size_t)capacity * 3; p.rad = base + (size_t)capacity * 4; p.sh_d = base + (size_t)capacity * 5;
+    p.sh_c = base + (size_t)capacity * 6; p.meta = base + (size_t)capacity * 7; p.aux = base + (size_t)capacity * 8;
+    p.capacity = capacity;
+    s->pool_capacity = capacity;
+    return LJ_OK;
+}
+
+struct EventPool {
+    std::vector<cudaEvent_t> ev;
+    size_t used = 0;
+    cudaEvent_t next() {
+        if (used == ev.size()) { cudaEvent_t e; cudaEventCreate(&e); ev.push_back(e); }
+        return ev[used++];
+    }
+    ~EventPool() { for (auto e : ev) cudaEventDestroy(e); }
+};
+
+static int render_impl(lj_scene *s, const lj_render_opts *opts_in, float *d_out, float *d_var, cudaStream_t stream, lj_stats *stats) {
+    lj_render_opts opts;
+    memset(&opts, 0, sizeof(opts));
+    if (opts_in) opts = *opts_in;
+    const DevScene &sc = s->dev;
+    if (sc.options.integrator != LJ_INT_PATH) {
+        set_error("integrator not supported by this build of the device path");
+        return LJ_ERR_UNSUPPORTED;
+    }
+    int spp = opts.spp > 0 ? opts.spp : sc.options.spp;
+    int sb = opts.sample_begin, se = opts.sample_end;
+    if (sb == 0 && se == 0) se = spp;
+    if (sb < 0 || se > spp || sb >= se) { set_error("bad sample range"); return LJ_ERR_INVALID; }
+    int w = sc.camera.width, h = sc.camera.height, npix = w * h;
+    int capacity = opts.pool_paths > 0 ? opts.pool_paths : (1 << 22);
+    {
+        // no point in holding more slots than there are samples
+        unsigned long long want = (unsigned long long)npix * (unsigned)(se - sb);
+        if (want < (unsigned long long)capacity) capacity = (int)((want + 255) / 256 * 256);
+    }
+    int r = ensure_pool(s, capacity);
+    if (r != LJ_OK) return r;
+    if (!s->d_film) LJ_CUDA(cudaMalloc(&s->d_film, (size_t)npix * 16));
+    if (d_var && !s->d_film_sq) LJ_CUDA(cudaMalloc(&s->d_film_sq, (size_t)npix * 16));
+    unsigned long long *d_counters = nullptr;
+    LJ_CUDA(cudaMalloc(&d_counters, sizeof(unsigned long long) * C_COUNT));
+    unsigned long long *h_counters = nullptr;
+    LJ_CUDA(cudaMallocHost(&h_counters, sizeof(unsigned long long) * C_COUNT));
+
+    WaveArgs a;
+    a.pool = s->pool;
+    a.rp.spp_total = (uint32_t)spp;
+    a.rp.sample_begin = (uint32_t)sb;
+    a.rp.sample_end = (uint32_t)se;
+    a.rp.seed = opts.seed ? opts.seed : kPcgDefaultSeed;
+    a.rp.width = w;
+    a.rp.height = h;
+    a.counters = d_counters;
+    a.film = s->d_film;
+    a.film_sq = d_var ? s->d_film_sq : nullptr;
+    a.tiles_x = (w + 7) / 8;
+    a.tiles_y = (h + 3) / 4;
+    a.total_items = (unsigned long long)a.tiles_x * a.tiles_y * 32ull * (unsigned)(se - sb);
+
+    const int nb256 = (capacity + 255) / 256, nb128 = (capacity + 127) / 128;
+    EventPool evp;
+    std::vector<cudaEvent_t> marks;  // 5 per wave: before regen, extend, shade, shadow, after shadow
+    uint64_t launches = 0, waves = 0;
+
+    cudaEvent_t ev_begin = evp.next(), ev_end = evp.next();
+    LJ_CUDA(cudaMemsetAsync(d_counters, 0, sizeof(unsigned long long) * C_COUNT, stream));
+    LJ_CUDA(cudaMemsetAsync(s->d_film, 0, (size_t)npix * 16, stream));
+    if (a.film_sq) LJ_CUDA(cudaMemsetAsync(s->d_film_sq, 0, (size_t)npix * 16, stream));
+    LJ_CUDA(cudaEventRecord(ev_begin, stream));
+    LJ_LAUNCH(k_clear_pool, nb256, 256, stream, s->pool);
+    launches++;
+    for (;;) {
+        cudaEvent_t e0 = evp.next(), e1 = evp.next(), e2 = evp.next(), e3 = evp.next(), e4 = evp.next();
+        LJ_CUDA(cudaMemsetAsync(&d_counters[C_ACTIVE], 0, sizeof(unsigned long long), stream));
+        LJ_CUDA(cudaEventRecord(e0, stream));
+        LJ_LAUNCH(k_regen, nb256, 256, stream, sc, a);
+        LJ_CUDA(cudaEventRecord(e1, stream));
+        LJ_CUDA(cudaMemcpyAsync(h_counters, d_counters, sizeof(unsigned long long) * C_COUNT, cudaMemcpyDeviceToHost, stream));
+        launches++;
+        LJ_CUDA(cudaStreamSynchronize(stream));
+        if (h_counters[C_ACTIVE] == 0) { marks.push_back(e0); marks.push_back(e1); marks.push_back(nullptr); break; }
+        LJ_LAUNCH(k_extend, nb256, 256, stream, sc, a);
+        LJ_CUDA(cudaEventRecord(e2, stream));
+        LJ_LAUNCH(k_shade, nb128, 128, stream, sc, a);
+        LJ_CUDA(cudaEventRecord(e3, stream));
+        LJ_LAUNCH(k_shadow, nb256, 256, stream, sc, a);
+        LJ_CUDA(cudaEventRecord(e4, stream));
+        launches += 3;
+        waves++;
+        marks.push_back(e0); marks.push_back(e1); marks.push_back(e2); marks.push_back(e3); marks.push_back(e4);
+        if (waves > 1000000) { set_error("wavefront loop did not terminate"); return LJ_ERR_CUDA; }
+    }
+    LJ_CUDA(cudaEventRecord(ev_end, stream));
+    LJ_LAUNCH(k_resolve, (npix + 255) / 256, 256, stream, s->d_film, a.film_sq, npix, 1.f / (float)(se - sb), opts.normalize, d_out, d_var);
+    launches++;
+    LJ_CUDA(cudaMemcpyAsync(h_counters, d_counters, sizeof(unsigned long long) * C_COUNT, cudaMemcpyDeviceToHost, stream));
+    LJ_CUDA(cudaStreamSynchronize(stream));
+    LJ_CUDA(cudaGetLastError());
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ev_begin, ev_end);
+        stats->render_ms = ms;
+        size_t k = 0;
+        while (k < marks.size()) {
+            if (k + 2 < marks.size() && marks[k + 2] == nullptr) {
+                cudaEventElapsedTime(&ms, marks[k], marks[k + 1]); stats->regen_ms += ms;
+                break;
+            }
+            cudaEventElapsedTime(&ms, marks[k], marks[k + 1]); stats->regen_ms += ms;
+            cudaEventElapsedTime(&ms, marks[k + 1], marks[k + 2]); stats->extend_ms += ms;
+            cudaEventElapsedTime(&ms, marks[k + 2], marks[k + 3]); stats->shade_ms += ms;
+            cudaEventElapsedTime(&ms, marks[k + 3], marks[k + 4]); stats->shadow_ms += ms;
+            k += 5;
+        }
+        stats->samples = h_counters[C_SAMPLES];
+        stats->closest_rays = h_counters[C_CLOSEST];
+        stats->shadow_rays = h_counters[C_SHADOW];
+        stats->bounces = h_counters[C_BOUNCES];
+        stats->kernel_launches = launches;
+        stats->waves = waves;
+        stats->extend_launches = stats->shade_launches = stats->shadow_launches = waves;
+        stats->regen_launches = waves + 1;
+    }
+    cudaFree(d_counters);
+    cudaFreeHost(h_counters);
+    return LJ_OK;
+}
+
+}  // namespace lj
+
+using namespace lj;
+
+extern "C" int lj_render_device(lj_scene *s, const lj_render_opts *opts, float *d_out_rgb, void *stream, lj_stats *stats) {
+    if (!s || !d_out_rgb) { set_error("null argument"); return LJ_ERR_INVALID; }
+    if (opts && opts->variance_out) { set_error("variance_out needs lj_render (host buffers)"); return LJ_ERR_INVALID; }
+    return render_impl(s, opts, d_out_rgb, nullptr, stream ? (cudaStream_t)stream : s->stream, stats);
+}
+
+extern "C" int lj_render(lj_scene *s, const lj_render_opts *opts, float *out_rgb, lj_stats *stats) {
+    if (!s || !out_rgb) { set_error("null argument"); return LJ_ERR_INVALID; }
+    int npix = s->dev.camera.width * s->dev.camera.height;
+    float *d_out = nullptr, *d_var = nullptr;
+    LJ_CUDA(cudaMalloc(&d_out, (size_t)npix * 3 * sizeof(float)));
+    bool want_var = opts && opts->variance_out;
+    if (want_var) LJ_CUDA(cudaMalloc(&d_var, (size_t)npix * 3 * sizeof(float)));
+    int r = render_impl(s, opts, d_out, d_var, s->stream, stats);
+    if (r == LJ_OK) {
+        cudaError_t e = cudaMemcpy(out_rgb, d_out, (size_t)npix * 3 * sizeof(float), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && want_var) e = cudaMemcpy(opts->variance_out, d_var, (size_t)npix * 3 * sizeof(float), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) r = cuda_fail(e, "framebuffer download");
+    }
+    cudaFree(d_out);
+    if (d_var) cudaFree(d_var);
+    return r;
+}

@@ -517,3 +517,13 @@ RTC_API void rtcOccluded1(RTCScene scene, struct RTCRay *ray, struct RTCOccluded
 }
 
 RTC_NAMESPACE_END
+
+// Ray counters (approximate to 1024 per thread) for the CPU-baseline Mrays/s figure.
+extern "C" void ljshim_get_counters(unsigned long long *closest, unsigned long long *any) {
+    *closest = g_closest.load();
+    *any = g_any.load();
+}
+extern "C" void ljshim_reset_counters(void) {
+    g_closest.store(0);
+    g_any.store(0);
+}
