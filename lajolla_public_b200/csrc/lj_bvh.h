@@ -79,6 +79,33 @@ LJ_HD bool hit_prim(const DevPrim *prims, int i, V3 o, V3 d, float tnear, float 
     return hit_triangle(xyz(a), mk3(a.w, b.x, b.y), mk3(b.z, b.w, c.x), o, d, tnear, tfar, t, u, v);
 }
 
+// Once the closest primitive is known its t is re-evaluated in fp64 on the same fp32 inputs: a grazing
+// ray makes the fp32 quotient dot(v0,Ng)/dot(Ng,d) lose half its digits, and the reference's double
+// shading code consumes that t (intersection.cpp:39-40).  One evaluation per ray, not per candidate.
+LJ_HD float refine_hit_t(const DevPrim *prims, int prim, V3 o, V3 d, float t32) {
+    V4 a = ld4(&prims[prim].a), b = ld4(&prims[prim].b), c = ld4(&prims[prim].c);
+    double ox = o.x, oy = o.y, oz = o.z, dx = d.x, dy = d.y, dz = d.z;
+    if (prim_is_sphere(c)) {
+        double fx = ox - a.x, fy = oy - a.y, fz = oz - a.z, r = a.w;
+        double A = dx * dx + dy * dy + dz * dz;
+        double bh = -(fx * dx + fy * dy + fz * dz);
+        double C = fx * fx + fy * fy + fz * fz - r * r;
+        double disc = bh * bh - A * C;
+        if (!(disc >= 0) || A == 0) return t32;
+        double q = bh + (bh >= 0 ? sqrt(disc) : -sqrt(disc));
+        double t0 = q != 0 ? C / q : 0, t1 = q / A;
+        // keep the root the fp32 test chose
+        return (float)(fabs(t0 - (double)t32) <= fabs(t1 - (double)t32) ? t0 : t1);
+    }
+    double v0x = a.x - ox, v0y = a.y - oy, v0z = a.z - oz;
+    double e0x = (double)b.z - a.x, e0y = (double)b.w - a.y, e0z = (double)c.x - a.z;   // v2 - v0
+    double e1x = (double)a.x - a.w, e1y = (double)a.y - b.x, e1z = (double)a.z - b.y;   // v0 - v1
+    double nx = e0y * e1z - e0z * e1y, ny = e0z * e1x - e0x * e1z, nz = e0x * e1y - e0y * e1x;
+    double den = nx * dx + ny * dy + nz * dz;
+    if (den == 0) return t32;
+    return (float)((v0x * nx + v0y * ny + v0z * nz) / den);
+}
+
 // Stack traversal of the binary BVH (DevNode2).  ANY = true stops at the first hit.
 // Edge-tie policy: a later candidate replaces the current hit only if strictly
 // nearer, so among exactly equal t the first one visited wins.
@@ -140,6 +167,7 @@ LJ_HD bool trace2(const DevNode2 *nodes, const DevPrim *prims, V3 o, V3 d, float
             node = stack[--sp];
         }
     }
+    if (!ANY && hit.prim != kNoHit) hit.t = refine_hit_t(prims, hit.prim, o, d, hit.t);
     return hit.prim != kNoHit;
 }
 

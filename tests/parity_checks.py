@@ -44,13 +44,12 @@ def check_ray_parity(scene, ref, rays, min_agree=0.9999, t_rel=1e-5):
     agree = same.mean()
     assert agree >= min_agree, f"hit primitive agreement {agree:.6f} < {min_agree}"
     hit = same & (h2["shape_id"] >= 0)
-    # t within 1e-5 relative.  Rays much shorter than the scene (corner bounces, t ~ 1e-5 R) carry the fp32
-    # round-off of the vertex coordinates themselves (ulp(|p|) ~ 1e-7 R), which no fp32 ray cast -- Embree's
-    # included -- can avoid; they get an absolute floor of 4e-6 R (R = bounding-sphere radius).
+    # t within 1e-5 relative for every agreeing ray (the device re-evaluates the winning primitive's t in
+    # fp64, lj_bvh.h refine_hit_t; the only slack is the fp32 storage of t, 1e-9 R).
     R = ref.info()["radius"]
     t2 = h2["t"][hit].astype(np.float64)
     aerr = np.abs(h1["t"][hit].astype(np.float64) - t2)
-    assert np.all(aerr <= t_rel * t2 + 4e-6 * R), f"t error {(aerr - t_rel * t2).max() / R:.3e} R beyond {t_rel} relative"
+    assert np.all(aerr <= t_rel * t2 + 1e-9 * R), f"t error {(aerr - t_rel * t2).max() / R:.3e} R beyond {t_rel} relative"
     terr = aerr / np.maximum(t2, 1e-2 * R)
     # barycentrics / sphere (u,v): the hit-point round-off (~1e-7 R) divided by the triangle's size, so small
     # triangles amplify it: median below 1e-5, 99.9 % below 2e-3.
