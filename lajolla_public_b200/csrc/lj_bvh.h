@@ -106,68 +106,98 @@ LJ_HD float refine_hit_t(const DevPrim *prims, int prim, V3 o, V3 d, float t32) 
     return (float)((v0x * nx + v0y * ny + v0z * nz) / den);
 }
 
-// Stack traversal of the binary BVH (DevNode2).  ANY = true stops at the first hit.
+// Stack traversal of the binary BVH (DevNode2), written as resumable steps so the persistent
+// kernels (wavefront.cu) can interleave traversal with fetching new rays into idle lanes.
 // Edge-tie policy: a later candidate replaces the current hit only if strictly
 // nearer, so among exactly equal t the first one visited wins.
 constexpr int kStackSize = 64;
+constexpr int kSentinel = 0x7fffffff;
+
+struct Trav {
+    V3 o, d, inv;
+    float tnear;
+    Hit hit;   // hit.t doubles as the current tfar
+    int node;  // >= 0 inner node, < 0 leaf, kSentinel = finished
+    int sp;
+    int stack[kStackSize];
+};
+
+LJ_HD void trav_init(Trav &tr, V3 o, V3 d, float tnear, float tfar) {
+    tr.o = o; tr.d = d;
+    tr.inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    tr.tnear = tnear;
+    tr.hit.prim = kNoHit; tr.hit.t = tfar; tr.hit.u = tr.hit.v = 0;
+    tr.sp = 0;
+    tr.stack[tr.sp++] = kSentinel;
+    tr.node = (tnear <= tfar) ? 0 : kSentinel;
+}
+
+// One inner-node step: slab tests of both children, descend into the nearer hit child.
+LJ_HD void trav_inner(const DevNode2 *nodes, Trav &tr) {
+    const int node = tr.node;
+    const V3 o = tr.o, inv = tr.inv;
+    V4 n0 = ld4(&nodes[node].n0), n1 = ld4(&nodes[node].n1);
+    V4 n2 = ld4(&nodes[node].n2), n3 = ld4(&nodes[node].n3);
+    float c0lox = (n0.x - o.x) * inv.x, c0hix = (n0.y - o.x) * inv.x;
+    float c0loy = (n0.z - o.y) * inv.y, c0hiy = (n0.w - o.y) * inv.y;
+    float c0loz = (n2.x - o.z) * inv.z, c0hiz = (n2.y - o.z) * inv.z;
+    float c1lox = (n1.x - o.x) * inv.x, c1hix = (n1.y - o.x) * inv.x;
+    float c1loy = (n1.z - o.y) * inv.y, c1hiy = (n1.w - o.y) * inv.y;
+    float c1loz = (n2.z - o.z) * inv.z, c1hiz = (n2.w - o.z) * inv.z;
+    float t0n = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), tr.tnear));
+    float t0f = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), tr.hit.t));
+    float t1n = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), tr.tnear));
+    float t1f = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), tr.hit.t));
+    // conservative: widen the far side by 2 ulp (Ize, "Robust BVH ray traversal")
+    bool h0 = t0n <= t0f * 1.0000004f;
+    bool h1 = t1n <= t1f * 1.0000004f;
+    int c0 = (int)f2u(n3.x), c1 = (int)f2u(n3.y);
+    if (h0 && h1) {
+        bool swap = t1n < t0n;
+        tr.node = swap ? c1 : c0;
+        if (tr.sp < kStackSize) tr.stack[tr.sp++] = swap ? c0 : c1;
+    } else if (h0) {
+        tr.node = c0;
+    } else if (h1) {
+        tr.node = c1;
+    } else {
+        tr.node = tr.stack[--tr.sp];
+    }
+}
+
+// Leaf step: test the leaf's primitives, then pop.  ANY: returns true (and stops) at the first hit.
+template <bool ANY>
+LJ_HD bool trav_leaf(const DevPrim *prims, Trav &tr) {
+    int v = ~tr.node;
+    int first = v >> 3, count = (v & 7) + 1;
+    for (int i = 0; i < count; i++) {
+        float t, uu, vv;
+        if (hit_prim(prims, first + i, tr.o, tr.d, tr.tnear, tr.hit.t, t, uu, vv)) {
+            if (ANY) { tr.hit.prim = first + i; tr.hit.t = t; tr.node = kSentinel; return true; }
+            if (t < tr.hit.t || tr.hit.prim == kNoHit) {
+                tr.hit.t = t; tr.hit.u = uu; tr.hit.v = vv; tr.hit.prim = first + i;
+            }
+        }
+    }
+    tr.node = tr.stack[--tr.sp];
+    return false;
+}
+
+// Closest hit: the winning primitive's t is refined in fp64 (see refine_hit_t).
+LJ_HD void trav_finish_closest(const DevPrim *prims, Trav &tr) {
+    if (tr.hit.prim != kNoHit) tr.hit.t = refine_hit_t(prims, tr.hit.prim, tr.o, tr.d, tr.hit.t);
+}
 
 template <bool ANY>
 LJ_HD bool trace2(const DevNode2 *nodes, const DevPrim *prims, V3 o, V3 d, float tnear, float tfar, Hit &hit) {
-    hit.prim = kNoHit;
-    hit.t = tfar;
-    hit.u = hit.v = 0;
-    if (!(tnear <= tfar)) return false;
-    V3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-    int stack[kStackSize];
-    int sp = 0;
-    int node = 0;
-    const int kSentinel = 0x7fffffff;
-    stack[sp++] = kSentinel;
-    while (node != kSentinel) {
-        if (node >= 0) {
-            V4 n0 = ld4(&nodes[node].n0), n1 = ld4(&nodes[node].n1);
-            V4 n2 = ld4(&nodes[node].n2), n3 = ld4(&nodes[node].n3);
-            float c0lox = (n0.x - o.x) * inv.x, c0hix = (n0.y - o.x) * inv.x;
-            float c0loy = (n0.z - o.y) * inv.y, c0hiy = (n0.w - o.y) * inv.y;
-            float c0loz = (n2.x - o.z) * inv.z, c0hiz = (n2.y - o.z) * inv.z;
-            float c1lox = (n1.x - o.x) * inv.x, c1hix = (n1.y - o.x) * inv.x;
-            float c1loy = (n1.z - o.y) * inv.y, c1hiy = (n1.w - o.y) * inv.y;
-            float c1loz = (n2.z - o.z) * inv.z, c1hiz = (n2.w - o.z) * inv.z;
-            float t0n = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), tnear));
-            float t0f = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), hit.t));
-            float t1n = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), tnear));
-            float t1f = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), hit.t));
-            // conservative: widen the far side by 2 ulp (Ize, "Robust BVH ray traversal")
-            bool h0 = t0n <= t0f * 1.0000004f;
-            bool h1 = t1n <= t1f * 1.0000004f;
-            int c0 = (int)f2u(n3.x), c1 = (int)f2u(n3.y);
-            if (h0 && h1) {
-                bool swap = t1n < t0n;
-                node = swap ? c1 : c0;
-                if (sp < kStackSize) stack[sp++] = swap ? c0 : c1;
-            } else if (h0) {
-                node = c0;
-            } else if (h1) {
-                node = c1;
-            } else {
-                node = stack[--sp];
-            }
-        } else {
-            int v = ~node;
-            int first = v >> 3, count = (v & 7) + 1;
-            for (int i = 0; i < count; i++) {
-                float t, uu, vv;
-                if (hit_prim(prims, first + i, o, d, tnear, hit.t, t, uu, vv)) {
-                    if (ANY) { hit.prim = first + i; hit.t = t; return true; }
-                    if (t < hit.t || hit.prim == kNoHit) {
-                        hit.t = t; hit.u = uu; hit.v = vv; hit.prim = first + i;
-                    }
-                }
-            }
-            node = stack[--sp];
-        }
+    Trav tr;
+    trav_init(tr, o, d, tnear, tfar);
+    while (tr.node != kSentinel) {
+        if (tr.node >= 0) trav_inner(nodes, tr);
+        else if (trav_leaf<ANY>(prims, tr)) break;
     }
-    if (!ANY && hit.prim != kNoHit) hit.t = refine_hit_t(prims, hit.prim, o, d, hit.t);
+    if (!ANY) trav_finish_closest(prims, tr);
+    hit = tr.hit;
     return hit.prim != kNoHit;
 }
 
