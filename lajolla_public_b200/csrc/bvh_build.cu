@@ -3,6 +3,8 @@
 // not on the per-sample path).
 #include "bvh_build.cuh"
 
+#include <stdlib.h>
+
 #if defined(LJ_HOSTSIM)
 #include <numeric>
 #include <vector>
@@ -68,10 +70,11 @@ __global__ void k_gather(const uint32_t *order, int n, const DevPrim *prims_unso
     leaf_box[i] = boxes[src];
 }
 
-__global__ void k_hierarchy(const uint64_t *keys, int n, int *left, int *right, int *parent_internal, int *parent_leaf) {
+__global__ void k_hierarchy(const uint64_t *keys, int n, int *left, int *right, int *parent_internal, int *parent_leaf,
+                            int *range_first, int *range_count) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
-    karras_node(keys, n, i, left, right, parent_internal, parent_leaf);
+    karras_node(keys, n, i, left, right, parent_internal, parent_leaf, range_first, range_count);
 }
 
 __global__ void k_refit(int n, const Box3 *leaf_box, Box3 *node_box, const int *left, const int *right,
@@ -81,10 +84,11 @@ __global__ void k_refit(int n, const Box3 *leaf_box, Box3 *node_box, const int *
     refit_from_leaf(k, leaf_box, node_box, left, right, parent_internal, parent_leaf, visit);
 }
 
-__global__ void k_emit2(int n_internal, const Box3 *leaf_box, const Box3 *node_box, const int *left, const int *right, DevNode2 *nodes) {
+__global__ void k_emit2(int n_internal, const Box3 *leaf_box, const Box3 *node_box, const int *left, const int *right,
+                        const int *range_first, const int *range_count, int max_leaf, DevNode2 *nodes) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_internal) return;
-    nodes[i] = emit_node2(i, leaf_box, node_box, left, right);
+    nodes[i] = emit_node2(i, leaf_box, node_box, left, right, range_first, range_count, max_leaf);
 }
 
 // SAH cost of the binary tree: sum over internal nodes of A(node)/A(root) * 1.2 + leaves * 1.0
@@ -107,9 +111,14 @@ cudaError_t dalloc(T **p, size_t n) { return cudaMalloc((void **)p, (n ? n : 1) 
 
 cudaError_t build_bvh2(const DevScene &sc, const int *d_prim_shape, const int *d_prim_local, int n,
                        cudaStream_t stream, BvhResult *out) {
+    // leaf size: LJ_BVH_MAX_LEAF in [1, 8] (default 4)
+    int max_leaf = 4;
+    if (const char *e = getenv("LJ_BVH_MAX_LEAF")) max_leaf = atoi(e);
+    max_leaf = max_leaf < 1 ? 1 : (max_leaf > 8 ? 8 : max_leaf);
     cudaError_t err = cudaSuccess;
     DevPrim *prims_unsorted = nullptr, *prims = nullptr;
     Box3 *boxes = nullptr, *leaf_box = nullptr, *node_box = nullptr;
+    int *range_first = nullptr, *range_count = nullptr;
     int *scene_bounds = nullptr, *left = nullptr, *right = nullptr, *parent_internal = nullptr, *parent_leaf = nullptr, *visit = nullptr;
     uint64_t *keys = nullptr, *keys_sorted = nullptr;
     uint32_t *vals = nullptr, *vals_sorted = nullptr;
@@ -129,6 +138,7 @@ cudaError_t build_bvh2(const DevScene &sc, const int *d_prim_shape, const int *d
     CK(dalloc(&parent_internal, n_internal)); CK(dalloc(&parent_leaf, n)); CK(dalloc(&visit, n_internal));
     CK(dalloc(&keys, n)); CK(dalloc(&keys_sorted, n)); CK(dalloc(&vals, n)); CK(dalloc(&vals_sorted, n));
     CK(dalloc(&nodes, n_internal)); CK(dalloc(&d_sah, 1));
+    CK(dalloc(&range_first, n_internal)); CK(dalloc(&range_count, n_internal));
     CK(cudaMemcpyAsync(scene_bounds, init_bounds, sizeof(init_bounds), cudaMemcpyHostToDevice, stream));
     CK(cudaMemsetAsync(parent_internal, 0xff, sizeof(int) * n_internal, stream));
     CK(cudaMemsetAsync(parent_leaf, 0xff, sizeof(int) * n, stream));
@@ -152,9 +162,9 @@ cudaError_t build_bvh2(const DevScene &sc, const int *d_prim_shape, const int *d
 #endif
     LJ_LAUNCH(k_gather, nb, T, stream, vals_sorted, n, prims_unsorted, boxes, prims, leaf_box);
     if (n > 1) {
-        LJ_LAUNCH(k_hierarchy, nb, T, stream, keys_sorted, n, left, right, parent_internal, parent_leaf);
+        LJ_LAUNCH(k_hierarchy, nb, T, stream, keys_sorted, n, left, right, parent_internal, parent_leaf, range_first, range_count);
         LJ_LAUNCH(k_refit, nb, T, stream, n, leaf_box, node_box, left, right, parent_internal, parent_leaf, visit);
-        LJ_LAUNCH(k_emit2, nb, T, stream, n - 1, leaf_box, node_box, left, right, nodes);
+        LJ_LAUNCH(k_emit2, nb, T, stream, n - 1, leaf_box, node_box, left, right, range_first, range_count, max_leaf, nodes);
         LJ_LAUNCH(k_sah, nb, T, stream, n - 1, node_box, leaf_box, n, d_sah);
         out->launches = 8;
     } else {
@@ -188,7 +198,7 @@ done:
     cudaFree(prims_unsorted); cudaFree(prims); cudaFree(boxes); cudaFree(leaf_box); cudaFree(node_box);
     cudaFree(scene_bounds); cudaFree(left); cudaFree(right); cudaFree(parent_internal); cudaFree(parent_leaf);
     cudaFree(visit); cudaFree(keys); cudaFree(keys_sorted); cudaFree(vals); cudaFree(vals_sorted);
-    cudaFree(cub_tmp); cudaFree(nodes); cudaFree(d_sah);
+    cudaFree(cub_tmp); cudaFree(nodes); cudaFree(d_sah); cudaFree(range_first); cudaFree(range_count);
     return err;
 }
 

@@ -118,6 +118,7 @@ struct Trav {
     float tnear;
     Hit hit;   // hit.t doubles as the current tfar
     int node;  // >= 0 inner node, < 0 leaf, kSentinel = finished
+    int leaf;  // postponed leaf (speculative while-while traversal), 0 = none
     int sp;
     int stack[kStackSize];
 };
@@ -128,6 +129,7 @@ LJ_HD void trav_init(Trav &tr, V3 o, V3 d, float tnear, float tfar) {
     tr.tnear = tnear;
     tr.hit.prim = kNoHit; tr.hit.t = tfar; tr.hit.u = tr.hit.v = 0;
     tr.sp = 0;
+    tr.leaf = 0;
     tr.stack[tr.sp++] = kSentinel;
     tr.node = (tnear <= tfar) ? 0 : kSentinel;
 }
@@ -165,20 +167,26 @@ LJ_HD void trav_inner(const DevNode2 *nodes, Trav &tr) {
     }
 }
 
-// Leaf step: test the leaf's primitives, then pop.  ANY: returns true (and stops) at the first hit.
+// Test the primitives of leaf reference `leaf`.  ANY: returns true at the first hit.
 template <bool ANY>
-LJ_HD bool trav_leaf(const DevPrim *prims, Trav &tr) {
-    int v = ~tr.node;
+LJ_HD bool trav_test_leaf(const DevPrim *prims, Trav &tr, int leaf) {
+    int v = ~leaf;
     int first = v >> 3, count = (v & 7) + 1;
     for (int i = 0; i < count; i++) {
         float t, uu, vv;
         if (hit_prim(prims, first + i, tr.o, tr.d, tr.tnear, tr.hit.t, t, uu, vv)) {
-            if (ANY) { tr.hit.prim = first + i; tr.hit.t = t; tr.node = kSentinel; return true; }
+            if (ANY) { tr.hit.prim = first + i; tr.hit.t = t; return true; }
             if (t < tr.hit.t || tr.hit.prim == kNoHit) {
                 tr.hit.t = t; tr.hit.u = uu; tr.hit.v = vv; tr.hit.prim = first + i;
             }
         }
     }
+    return false;
+}
+// Leaf step of the plain loop: test tr.node's primitives, then pop.
+template <bool ANY>
+LJ_HD bool trav_leaf(const DevPrim *prims, Trav &tr) {
+    if (trav_test_leaf<ANY>(prims, tr, tr.node)) { tr.node = kSentinel; return true; }
     tr.node = tr.stack[--tr.sp];
     return false;
 }

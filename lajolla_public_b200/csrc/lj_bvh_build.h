@@ -105,7 +105,8 @@ LJ_HD int karras_delta(const uint64_t *keys, int n, int i, int j) {
 
 // Internal node i of n-1: children and parent links.  child encoding here: >=0 internal, <0 leaf ~k
 // (k = position in sorted order).
-LJ_HD void karras_node(const uint64_t *keys, int n, int i, int *left, int *right, int *parent_internal, int *parent_leaf) {
+LJ_HD void karras_node(const uint64_t *keys, int n, int i, int *left, int *right, int *parent_internal, int *parent_leaf,
+                       int *range_first, int *range_count) {
     int d = karras_delta(keys, n, i, i + 1) - karras_delta(keys, n, i, i - 1) >= 0 ? 1 : -1;
     int dmin = karras_delta(keys, n, i, i - d);
     int lmax = 2;
@@ -127,6 +128,8 @@ LJ_HD void karras_node(const uint64_t *keys, int n, int i, int *left, int *right
     int rc = (hi == gamma + 1) ? ~(gamma + 1) : gamma + 1;
     left[i] = lc;
     right[i] = rc;
+    range_first[i] = lo;          // the subtree of node i covers sorted primitives [lo, hi]
+    range_count[i] = hi - lo + 1;
     if (lc >= 0) parent_internal[lc] = i; else parent_leaf[~lc] = i;
     if (rc >= 0) parent_internal[rc] = i; else parent_leaf[~rc] = i;
 }
@@ -147,13 +150,17 @@ LJ_HD void refit_from_leaf(int k, const Box3 *leaf_box, Box3 *node_box, const in
     }
 }
 
-// Emit the traversal node of internal node i (children's boxes stored in the parent).
-LJ_HD DevNode2 emit_node2(int i, const Box3 *leaf_box, const Box3 *node_box, const int *left, const int *right) {
+// Emit the traversal node of internal node i (children's boxes stored in the parent).  A child
+// subtree holding at most max_leaf primitives is collapsed into one leaf: Karras subtrees cover a
+// contiguous range of the sorted primitive array, so the leaf is just (first, count).
+LJ_HD int leaf_ref(int first, int count) { return ~((first << 3) | (count - 1)); }
+LJ_HD DevNode2 emit_node2(int i, const Box3 *leaf_box, const Box3 *node_box, const int *left, const int *right,
+                          const int *range_first, const int *range_count, int max_leaf) {
     int lc = left[i], rc = right[i];
     Box3 lb = lc >= 0 ? node_box[lc] : leaf_box[~lc];
     Box3 rb = rc >= 0 ? node_box[rc] : leaf_box[~rc];
-    int c0 = lc >= 0 ? lc : ~(((~lc) << 3) | 0);
-    int c1 = rc >= 0 ? rc : ~(((~rc) << 3) | 0);
+    int c0 = lc >= 0 ? (range_count[lc] <= max_leaf ? leaf_ref(range_first[lc], range_count[lc]) : lc) : leaf_ref(~lc, 1);
+    int c1 = rc >= 0 ? (range_count[rc] <= max_leaf ? leaf_ref(range_first[rc], range_count[rc]) : rc) : leaf_ref(~rc, 1);
     DevNode2 nd;
     nd.n0 = mk4(lb.lo.x, lb.hi.x, lb.lo.y, lb.hi.y);
     nd.n1 = mk4(rb.lo.x, rb.hi.x, rb.lo.y, rb.hi.y);

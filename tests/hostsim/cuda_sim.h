@@ -85,3 +85,4 @@ inline float lj_warp_max(float x) { return x; }
 inline double lj_warp_sum(double x) { return x; }
 inline int lj_float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
 inline unsigned __activemask() { return 1u; }
+inline bool __any_sync(unsigned, bool p) { return p; }
