@@ -161,7 +161,7 @@ typedef struct lj_scene lj_scene; /* opaque, device-resident */
 typedef struct lj_render_opts {
     int32_t spp;           /* <=0: use the scene's samples_per_pixel */
     int32_t sample_begin;  /* this call renders samples [sample_begin, sample_end) of every pixel; */
-    int32_t sample_end;    /* both 0 => [0, spp).  Path stream id = pixel*spp + sample (pcg.h:33) */
+    int32_t sample_end;    /* both 0 => [0, spp).  PCG stream of a path = hash(pixel*spp + sample)    */
     int32_t normalize;     /* 1: divide by (sample_end-sample_begin) like render.cpp:94; 0: raw sums */
     int32_t pool_paths;    /* path slots resident in HBM; <=0: default (1<<22) */
     uint64_t seed;         /* 0 => pcg.h:33 default seed */
@@ -258,7 +258,7 @@ int lj_pcg32_batch(uint64_t first_stream, uint64_t seed, int32_t n_streams, int3
 
 /* ---- introspection -------------------------------------------------------------------------- */
 typedef struct lj_scene_info {
-    int32_t num_prims, num_triangles, num_spheres, num_bvh_nodes, bvh_width;
+    int32_t num_prims, num_triangles, num_spheres, num_bvh_nodes, bvh_width, bvh_depth;
     float bounds_lo[3], bounds_hi[3];
     float bsphere_radius, bsphere_center[3]; /* scene.cpp:29-34 */
     float shadow_epsilon;                    /* scene.h:99-105 */

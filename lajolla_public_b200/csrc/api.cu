@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(256) k_trace_closest(const LJ_GRID_CONSTANT De
     lj_ray r = rays[i];
     V3 o = mk3(r.org[0], r.org[1], r.org[2]), d = mk3(r.dir[0], r.dir[1], r.dir[2]);
     Hit h;
-    trace2<false>(sc.nodes2, sc.prims, o, d, r.tnear, r.tfar, h);
+    trace8<false>(sc.nodes8, sc.prims, o, d, r.tnear, r.tfar, h);
     lj_hit out;
     hit_to_abi(sc, o, d, h, out);
     hits[i] = out;
@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(256) k_trace_any(const LJ_GRID_CONSTANT DevSce
     if (i >= n) return;
     lj_ray r = rays[i];
     Hit h;
-    occ[i] = trace2<true>(sc.nodes2, sc.prims, mk3(r.org[0], r.org[1], r.org[2]), mk3(r.dir[0], r.dir[1], r.dir[2]), r.tnear, r.tfar, h) ? 1 : 0;
+    occ[i] = trace8<true>(sc.nodes8, sc.prims, mk3(r.org[0], r.org[1], r.org[2]), mk3(r.dir[0], r.dir[1], r.dir[2]), r.tnear, r.tfar, h) ? 1 : 0;
 }
 
 LJ_HD void v3_out(float *o, V3 v) { o[0] = v.x; o[1] = v.y; o[2] = v.z; }
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(128) k_intersect(const LJ_GRID_CONSTANT DevSce
     lj_vertex ov;
     memset(&ov, 0, sizeof(ov));
     ov.shape_id = ov.primitive_id = ov.material_id = ov.interior_medium_id = ov.exterior_medium_id = -1;
-    if (trace2<false>(sc.nodes2, sc.prims, o, d, r.tnear, r.tfar, h)) {
+    if (trace8<false>(sc.nodes8, sc.prims, o, d, r.tnear, r.tfar, h)) {
         Vertex v = make_vertex(sc, o, d, h, rd ? rd[2 * i] : 0.f, rd ? rd[2 * i + 1] : 0.f);
         vertex_to_abi(v, ov);
     }

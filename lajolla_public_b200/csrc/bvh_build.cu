@@ -5,11 +5,14 @@
 
 #include <stdlib.h>
 
+#include <utility>
+
 #if defined(LJ_HOSTSIM)
 #include <numeric>
 #include <vector>
 #else
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #endif
 
 namespace lj {
@@ -62,42 +65,49 @@ __global__ void k_morton(const Box3 *boxes, int n, const int *scene_bounds, uint
     vals[i] = (uint32_t)i;
 }
 
-__global__ void k_gather(const uint32_t *order, int n, const DevPrim *prims_unsorted, const Box3 *boxes, DevPrim *prims, Box3 *leaf_box) {
+// Morton order: primitive records and their boxes become tree leaves 0..n-1; every leaf is its own cluster.
+__global__ void k_gather(const uint32_t *order, int n, const DevPrim *prims_unsorted, const Box3 *boxes, DevPrim *prims_sorted,
+                         Tree2 tree, int *cluster) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t src = order[i];
-    prims[i] = prims_unsorted[src];
-    leaf_box[i] = boxes[src];
+    prims_sorted[i] = prims_unsorted[src];
+    tree.box[i] = boxes[src];
+    tree.count[i] = 1;
+    cluster[i] = i;
 }
 
-__global__ void k_hierarchy(const uint64_t *keys, int n, int *left, int *right, int *parent_internal, int *parent_leaf,
-                            int *range_first, int *range_count) {
+__global__ void k_ploc_nearest(Tree2 tree, const int *cluster, int m, int radius, int *nearest) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n - 1) return;
-    karras_node(keys, n, i, left, right, parent_internal, parent_leaf, range_first, range_count);
+    if (i >= m) return;
+    nearest[i] = ploc_nearest(tree, cluster, m, i, radius);
 }
 
-__global__ void k_refit(int n, const Box3 *leaf_box, Box3 *node_box, const int *left, const int *right,
-                        const int *parent_internal, const int *parent_leaf, int *visit) {
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    refit_from_leaf(k, leaf_box, node_box, left, right, parent_internal, parent_leaf, visit);
-}
-
-__global__ void k_emit2(int n_internal, const Box3 *leaf_box, const Box3 *node_box, const int *left, const int *right,
-                        const int *range_first, const int *range_count, int max_leaf, DevNode2 *nodes) {
+__global__ void k_ploc_merge(Tree2 tree, const int *cluster, const int *nearest, int m, int *next_node, int *cluster_tmp, int *keep) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_internal) return;
-    nodes[i] = emit_node2(i, leaf_box, node_box, left, right, range_first, range_count, max_leaf);
+    if (i >= m) return;
+    keep[i] = ploc_merge(tree, cluster, nearest, i, next_node, cluster_tmp);
+}
+
+__global__ void k_ploc_compact(const int *cluster_tmp, const int *keep, const int *offset, int m, int *cluster_out, int *m_out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    if (keep[i]) cluster_out[offset[i]] = cluster_tmp[i];
+    if (i == m - 1) *m_out = offset[i] + keep[i];
+}
+
+__global__ void k_collapse(CollapseCtx ctx, const CollapseItem *queue_in, int count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    collapse_node(ctx, queue_in[i]);
 }
 
 // SAH cost of the binary tree: sum over internal nodes of A(node)/A(root) * 1.2 + leaves * 1.0
-__global__ void k_sah(int n_internal, const Box3 *node_box, const Box3 *leaf_box, int n, double *out) {
+__global__ void k_sah(Tree2 tree, int root, double *out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     double c = 0;
-    float root = box_half_area(node_box[0]);
-    if (i < n_internal) c += 1.2 * box_half_area(node_box[i]) / root;
-    if (i < n) c += 1.0 * box_half_area(leaf_box[i]) / root;
+    float ra = box_half_area(tree.box[root]);
+    if (i < 2 * tree.n - 1 && ra > 0) c = (i < tree.n ? 1.0 : 1.2) * box_half_area(tree.box[i]) / ra;
     c = lj_warp_sum(c);
     if (LJ_LANE() == 0 && c != 0) atomicAdd(out, c);
 }
@@ -109,41 +119,55 @@ cudaError_t dalloc(T **p, size_t n) { return cudaMalloc((void **)p, (n ? n : 1) 
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { err = e_; goto done; } } while (0)
 
-cudaError_t build_bvh2(const DevScene &sc, const int *d_prim_shape, const int *d_prim_local, int n,
+static cudaError_t exclusive_scan(void *tmp, size_t &tmp_bytes, const int *in, int *out, int m, cudaStream_t stream) {
+#if defined(LJ_HOSTSIM)
+    (void)tmp; (void)stream;
+    tmp_bytes = 1;
+    if (in) { int acc = 0; for (int i = 0; i < m; i++) { out[i] = acc; acc += in[i]; } }
+    return cudaSuccess;
+#else
+    return cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, in, out, m, stream);
+#endif
+}
+
+cudaError_t build_bvh8(const DevScene &sc, const int *d_prim_shape, const int *d_prim_local, int n,
                        cudaStream_t stream, BvhResult *out) {
-    // leaf size: LJ_BVH_MAX_LEAF in [1, 8] (default 4)
-    int max_leaf = 4;
-    if (const char *e = getenv("LJ_BVH_MAX_LEAF")) max_leaf = atoi(e);
-    max_leaf = max_leaf < 1 ? 1 : (max_leaf > 8 ? 8 : max_leaf);
+    // search radius of the PLOC neighbour search: LJ_PLOC_RADIUS in [1, 64] (default 16)
+    int radius = 16;
+    if (const char *e = getenv("LJ_PLOC_RADIUS")) radius = atoi(e);
+    radius = radius < 1 ? 1 : (radius > 64 ? 64 : radius);
     cudaError_t err = cudaSuccess;
-    DevPrim *prims_unsorted = nullptr, *prims = nullptr;
-    Box3 *boxes = nullptr, *leaf_box = nullptr, *node_box = nullptr;
-    int *range_first = nullptr, *range_count = nullptr;
-    int *scene_bounds = nullptr, *left = nullptr, *right = nullptr, *parent_internal = nullptr, *parent_leaf = nullptr, *visit = nullptr;
+    DevPrim *prims_unsorted = nullptr, *prims_sorted = nullptr, *prims = nullptr;
+    Box3 *boxes = nullptr;
+    Tree2 tree = {nullptr, nullptr, nullptr, nullptr, n};
+    int *scene_bounds = nullptr, *cluster_a = nullptr, *cluster_b = nullptr, *cluster_tmp = nullptr, *nearest = nullptr;
+    int *keep = nullptr, *offset = nullptr, *d_ints = nullptr;  // d_ints: [0] next binary node, [1] cluster count, [2..5] collapse counters
     uint64_t *keys = nullptr, *keys_sorted = nullptr;
     uint32_t *vals = nullptr, *vals_sorted = nullptr;
-    void *cub_tmp = nullptr;
-    size_t cub_bytes = 0;
-    DevNode2 *nodes = nullptr;
+    CollapseItem *queue_a = nullptr, *queue_b = nullptr;
+    void *cub_tmp = nullptr, *scan_tmp = nullptr;
+    size_t cub_bytes = 0, scan_bytes = 0;
+    DevNode8 *nodes = nullptr;
     double *d_sah = nullptr;
     const int T = 256;
     const int nb = (n + T - 1) / T;
-    const int n_internal = n > 1 ? n - 1 : 1;
-    int h_bounds[6];
+    const int n_tree = 2 * n - 1;
+    const int max_nodes8 = n > 1 ? n - 1 : 1;
+    int h_bounds[6], h_ints[6];
     int init_bounds[6] = {0x7fffffff, 0x7fffffff, 0x7fffffff, (int)0x80000000, (int)0x80000000, (int)0x80000000};
+    int m = n, root2 = 0, launches = 0, rounds = 0, levels = 0;
 
-    CK(dalloc(&prims_unsorted, n)); CK(dalloc(&prims, n));
-    CK(dalloc(&boxes, n)); CK(dalloc(&leaf_box, n)); CK(dalloc(&node_box, n_internal));
-    CK(dalloc(&scene_bounds, 6)); CK(dalloc(&left, n_internal)); CK(dalloc(&right, n_internal));
-    CK(dalloc(&parent_internal, n_internal)); CK(dalloc(&parent_leaf, n)); CK(dalloc(&visit, n_internal));
+    CK(dalloc(&prims_unsorted, n)); CK(dalloc(&prims_sorted, n)); CK(dalloc(&prims, n));
+    CK(dalloc(&boxes, n)); CK(dalloc(&tree.box, n_tree)); CK(dalloc(&tree.left, n_tree)); CK(dalloc(&tree.right, n_tree));
+    CK(dalloc(&tree.count, n_tree));
+    CK(dalloc(&scene_bounds, 6)); CK(dalloc(&cluster_a, n)); CK(dalloc(&cluster_b, n)); CK(dalloc(&cluster_tmp, n));
+    CK(dalloc(&nearest, n)); CK(dalloc(&keep, n)); CK(dalloc(&offset, n)); CK(dalloc(&d_ints, 6));
     CK(dalloc(&keys, n)); CK(dalloc(&keys_sorted, n)); CK(dalloc(&vals, n)); CK(dalloc(&vals_sorted, n));
-    CK(dalloc(&nodes, n_internal)); CK(dalloc(&d_sah, 1));
-    CK(dalloc(&range_first, n_internal)); CK(dalloc(&range_count, n_internal));
+    CK(dalloc(&queue_a, n)); CK(dalloc(&queue_b, n));
+    CK(dalloc(&nodes, max_nodes8)); CK(dalloc(&d_sah, 1));
     CK(cudaMemcpyAsync(scene_bounds, init_bounds, sizeof(init_bounds), cudaMemcpyHostToDevice, stream));
-    CK(cudaMemsetAsync(parent_internal, 0xff, sizeof(int) * n_internal, stream));
-    CK(cudaMemsetAsync(parent_leaf, 0xff, sizeof(int) * n, stream));
-    CK(cudaMemsetAsync(visit, 0, sizeof(int) * n_internal, stream));
     CK(cudaMemsetAsync(d_sah, 0, sizeof(double), stream));
+    CK(cudaMemsetAsync(nodes, 0, sizeof(DevNode8) * max_nodes8, stream));
 
     LJ_LAUNCH(k_prim_boxes, nb, T, stream, sc, d_prim_shape, d_prim_local, n, prims_unsorted, boxes, scene_bounds);
     LJ_LAUNCH(k_morton, nb, T, stream, boxes, n, scene_bounds, keys, vals);
@@ -160,26 +184,56 @@ cudaError_t build_bvh2(const DevScene &sc, const int *d_prim_shape, const int *d
     CK(cudaMalloc(&cub_tmp, cub_bytes ? cub_bytes : 1));
     CK(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, keys, keys_sorted, vals, vals_sorted, n, 0, 63, stream));
 #endif
-    LJ_LAUNCH(k_gather, nb, T, stream, vals_sorted, n, prims_unsorted, boxes, prims, leaf_box);
-    if (n > 1) {
-        LJ_LAUNCH(k_hierarchy, nb, T, stream, keys_sorted, n, left, right, parent_internal, parent_leaf, range_first, range_count);
-        LJ_LAUNCH(k_refit, nb, T, stream, n, leaf_box, node_box, left, right, parent_internal, parent_leaf, visit);
-        LJ_LAUNCH(k_emit2, nb, T, stream, n - 1, leaf_box, node_box, left, right, range_first, range_count, max_leaf, nodes);
-        LJ_LAUNCH(k_sah, nb, T, stream, n - 1, node_box, leaf_box, n, d_sah);
-        out->launches = 8;
-    } else {
-        // single primitive: node 0 = { leaf 0, empty box }
-        Box3 lb;
-        CK(cudaMemcpyAsync(&lb, leaf_box, sizeof(Box3), cudaMemcpyDeviceToHost, stream));
+    LJ_LAUNCH(k_gather, nb, T, stream, vals_sorted, n, prims_unsorted, boxes, prims_sorted, tree, cluster_a);
+    launches = 5;
+
+    // ---- PLOC rounds: nearest neighbour -> merge mutual pairs -> order-preserving compaction
+    h_ints[0] = n; h_ints[1] = n;
+    CK(cudaMemcpyAsync(d_ints, h_ints, 2 * sizeof(int), cudaMemcpyHostToDevice, stream));
+    CK(exclusive_scan(nullptr, scan_bytes, nullptr, offset, n, stream));
+    CK(cudaMalloc(&scan_tmp, scan_bytes ? scan_bytes : 1));
+    while (m > 1) {
+        int g = (m + T - 1) / T;
+        LJ_LAUNCH(k_ploc_nearest, g, T, stream, tree, cluster_a, m, radius, nearest);
+        LJ_LAUNCH(k_ploc_merge, g, T, stream, tree, cluster_a, nearest, m, d_ints + 0, cluster_tmp, keep);
+        CK(exclusive_scan(scan_tmp, scan_bytes, keep, offset, m, stream));
+        LJ_LAUNCH(k_ploc_compact, g, T, stream, cluster_tmp, keep, offset, m, cluster_b, d_ints + 1);
+        CK(cudaMemcpyAsync(h_ints, d_ints, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
-        DevNode2 nd;
-        float inf = INFINITY;
-        nd.n0 = mk4(lb.lo.x, lb.hi.x, lb.lo.y, lb.hi.y);
-        nd.n1 = mk4(inf, -inf, inf, -inf);
-        nd.n2 = mk4(lb.lo.z, lb.hi.z, inf, -inf);
-        nd.n3 = mk4(u2f((uint32_t)~0), u2f((uint32_t)~0), 0.f, 0.f);
-        CK(cudaMemcpyAsync(nodes, &nd, sizeof(nd), cudaMemcpyHostToDevice, stream));
-        out->launches = 4;
+        if (h_ints[1] >= m || h_ints[1] < 1) { err = cudaErrorUnknown; goto done; }  // every round merges at least one pair
+        m = h_ints[1];
+        std::swap(cluster_a, cluster_b);
+        launches += 4;
+        rounds++;
+    }
+    root2 = n > 1 ? 2 * n - 2 : 0;
+    LJ_LAUNCH(k_sah, (n_tree + T - 1) / T, T, stream, tree, root2, d_sah);
+
+    // ---- collapse, one level of wide nodes per launch
+    {
+        CollapseCtx ctx;
+        ctx.tree = tree;
+        ctx.prims_sorted = prims_sorted;
+        ctx.prims_out = prims;
+        ctx.nodes8 = nodes;
+        ctx.counters = d_ints + 2;
+        CollapseItem first = {root2, 0, 1, 0};
+        int init[4] = {1, 0, 0, 0};
+        CK(cudaMemcpyAsync(queue_a, &first, sizeof(first), cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(d_ints + 2, init, sizeof(init), cudaMemcpyHostToDevice, stream));
+        int count = 1;
+        while (count > 0) {
+            ctx.queue_out = queue_b;
+            CK(cudaMemsetAsync(d_ints + 5, 0, sizeof(int), stream));
+            LJ_LAUNCH(k_collapse, (count + 63) / 64, 64, stream, ctx, queue_a, count);
+            CK(cudaMemcpyAsync(h_ints + 2, d_ints + 2, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
+            count = h_ints[5];
+            std::swap(queue_a, queue_b);
+            launches++;
+            levels++;
+            if (levels > 4096) { err = cudaErrorUnknown; goto done; }
+        }
     }
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(h_bounds, scene_bounds, sizeof(h_bounds), cudaMemcpyDeviceToHost, stream));
@@ -191,14 +245,21 @@ cudaError_t build_bvh2(const DevScene &sc, const int *d_prim_shape, const int *d
     }
     out->nodes = nodes;
     out->prims = prims;
-    out->num_nodes = n_internal;
+    out->num_nodes = h_ints[2];
+    out->num_prims_placed = h_ints[3];
+    out->depth = h_ints[4];
+    out->ploc_rounds = rounds;
+    out->launches = launches + 1;
     nodes = nullptr;
     prims = nullptr;
 done:
-    cudaFree(prims_unsorted); cudaFree(prims); cudaFree(boxes); cudaFree(leaf_box); cudaFree(node_box);
-    cudaFree(scene_bounds); cudaFree(left); cudaFree(right); cudaFree(parent_internal); cudaFree(parent_leaf);
-    cudaFree(visit); cudaFree(keys); cudaFree(keys_sorted); cudaFree(vals); cudaFree(vals_sorted);
-    cudaFree(cub_tmp); cudaFree(nodes); cudaFree(d_sah); cudaFree(range_first); cudaFree(range_count);
+    cudaFree(prims_unsorted); cudaFree(prims_sorted); cudaFree(prims); cudaFree(boxes);
+    cudaFree(tree.box); cudaFree(tree.left); cudaFree(tree.right); cudaFree(tree.count);
+    cudaFree(scene_bounds); cudaFree(cluster_a); cudaFree(cluster_b); cudaFree(cluster_tmp); cudaFree(nearest);
+    cudaFree(keep); cudaFree(offset); cudaFree(d_ints);
+    cudaFree(keys); cudaFree(keys_sorted); cudaFree(vals); cudaFree(vals_sorted);
+    cudaFree(queue_a); cudaFree(queue_b);
+    cudaFree(cub_tmp); cudaFree(scan_tmp); cudaFree(nodes); cudaFree(d_sah);
     return err;
 }
 

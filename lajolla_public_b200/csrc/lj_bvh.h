@@ -106,103 +106,187 @@ LJ_HD float refine_hit_t(const DevPrim *prims, int prim, V3 o, V3 d, float t32) 
     return (float)((v0x * nx + v0y * ny + v0z * nz) / den);
 }
 
-// Stack traversal of the binary BVH (DevNode2), written as resumable steps so the persistent
-// kernels (wavefront.cu) can interleave traversal with fetching new rays into idle lanes.
+// Stack traversal of the 8-wide compressed BVH (DevNode8, lj_scene_dev.h), after Ylitie, Karras &
+// Laine 2017.  State is a pair of "groups": G = (child node base, hit bits << 24 | imask) names the
+// still-unvisited hit children of one node, Gt = (primitive base, 24 hit bits) the primitives of its
+// hit leaf slots.  Children are visited highest bit first; a node's children sit in octant-ordered
+// slots (lj_bvh_build.h) and the bit of slot s is 24 + (s ^ octinv), so front-to-back order comes
+// from the ray's sign octant alone and no distances are sorted.  Written as resumable steps so the
+// persistent kernels (wavefront.cu) can interleave traversal with fetching new rays into idle lanes.
 // Edge-tie policy: a later candidate replaces the current hit only if strictly
 // nearer, so among exactly equal t the first one visited wins.
-constexpr int kStackSize = 64;
-constexpr int kSentinel = 0x7fffffff;
+constexpr int kStack8 = 48;         // entries; node groups need <= tree depth (checked at build, <= 30)
+constexpr int kTriPostponeMax = 16; // primitive groups are postponed only below this fill level
+
+struct U2 { uint32_t x, y; };
+
+LJ_HD int bfind32(uint32_t v) {  // index of the highest set bit, v != 0
+#if defined(__CUDA_ARCH__)
+    return 31 - __clz((int)v);
+#else
+    return 31 - __builtin_clz(v);
+#endif
+}
+LJ_HD int popc32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return __popc(v);
+#else
+    return __builtin_popcount(v);
+#endif
+}
+// per byte: 0xff where the byte's top bit is set
+LJ_HD uint32_t sign_extend_s8x4(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    uint32_t r;  // PRMT with the sign-replicate bit set in every selector nibble (__byte_perm masks that bit off)
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(v), "r"(0u), "r"(0x0000ba98u));
+    return r;
+#else
+    return ((v >> 7) & 0x01010101u) * 0xffu;
+#endif
+}
+LJ_HD float byte_f(uint32_t v, int i) { return (float)((v >> (8 * i)) & 0xffu); }
 
 struct Trav {
-    V3 o, d, inv;
+    V3 o, d;
+    V3 idir;       // 1/d with |d| clamped away from 0
     float tnear;
-    Hit hit;   // hit.t doubles as the current tfar
-    int node;  // >= 0 inner node, < 0 leaf, kSentinel = finished
-    int leaf;  // postponed leaf (speculative while-while traversal), 0 = none
+    Hit hit;       // hit.t doubles as the current tfar
+    uint32_t octinv4;
+    U2 G, Gt;      // current node group / primitive group (y == 0: empty)
     int sp;
-    int stack[kStackSize];
+    U2 stack[kStack8];
 };
+
+LJ_HD bool trav_done(const Trav &tr) { return (tr.G.y & 0xff000000u) == 0 && tr.Gt.y == 0 && tr.sp == 0; }
 
 LJ_HD void trav_init(Trav &tr, V3 o, V3 d, float tnear, float tfar) {
     tr.o = o; tr.d = d;
-    tr.inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    const float tiny = 8.271806e-25f;  // 2^-80: keeps 2^e * idir finite for any node scale
+    tr.idir = mk3(1.0f / (fabsf(d.x) > tiny ? d.x : copysignf(tiny, d.x)),
+                  1.0f / (fabsf(d.y) > tiny ? d.y : copysignf(tiny, d.y)),
+                  1.0f / (fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z)));
     tr.tnear = tnear;
     tr.hit.prim = kNoHit; tr.hit.t = tfar; tr.hit.u = tr.hit.v = 0;
+    uint32_t oct = (d.x < 0 ? 1u : 0u) | (d.y < 0 ? 2u : 0u) | (d.z < 0 ? 4u : 0u);
+    tr.octinv4 = (7u ^ oct) * 0x01010101u;
     tr.sp = 0;
-    tr.leaf = 0;
-    tr.stack[tr.sp++] = kSentinel;
-    tr.node = (tnear <= tfar) ? 0 : kSentinel;
+    tr.Gt.x = 0; tr.Gt.y = 0;
+    // root group: one hit bit and an empty imask, so trav_node resolves it to node 0 whatever the octant
+    tr.G.x = 0;
+    tr.G.y = (tnear <= tfar) ? 0x80000000u : 0u;
 }
 
-// One inner-node step: slab tests of both children, descend into the nearer hit child.
-LJ_HD void trav_inner(const DevNode2 *nodes, Trav &tr) {
-    const int node = tr.node;
-    const V3 o = tr.o, inv = tr.inv;
-    V4 n0 = ld4(&nodes[node].n0), n1 = ld4(&nodes[node].n1);
-    V4 n2 = ld4(&nodes[node].n2), n3 = ld4(&nodes[node].n3);
-    float c0lox = (n0.x - o.x) * inv.x, c0hix = (n0.y - o.x) * inv.x;
-    float c0loy = (n0.z - o.y) * inv.y, c0hiy = (n0.w - o.y) * inv.y;
-    float c0loz = (n2.x - o.z) * inv.z, c0hiz = (n2.y - o.z) * inv.z;
-    float c1lox = (n1.x - o.x) * inv.x, c1hix = (n1.y - o.x) * inv.x;
-    float c1loy = (n1.z - o.y) * inv.y, c1hiy = (n1.w - o.y) * inv.y;
-    float c1loz = (n2.z - o.z) * inv.z, c1hiz = (n2.w - o.z) * inv.z;
-    float t0n = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), tr.tnear));
-    float t0f = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), tr.hit.t));
-    float t1n = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), tr.tnear));
-    float t1f = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), tr.hit.t));
-    // conservative: widen the far side by 2 ulp (Ize, "Robust BVH ray traversal")
-    bool h0 = t0n <= t0f * 1.0000004f;
-    bool h1 = t1n <= t1f * 1.0000004f;
-    int c0 = (int)f2u(n3.x), c1 = (int)f2u(n3.y);
-    if (h0 && h1) {
-        bool swap = t1n < t0n;
-        tr.node = swap ? c1 : c0;
-        if (tr.sp < kStackSize) tr.stack[tr.sp++] = swap ? c0 : c1;
-    } else if (h0) {
-        tr.node = c0;
-    } else if (h1) {
-        tr.node = c1;
-    } else {
-        tr.node = tr.stack[--tr.sp];
-    }
-}
-
-// Test the primitives of leaf reference `leaf`.  ANY: returns true at the first hit.
-template <bool ANY>
-LJ_HD bool trav_test_leaf(const DevPrim *prims, Trav &tr, int leaf) {
-    int v = ~leaf;
-    int first = v >> 3, count = (v & 7) + 1;
-    for (int i = 0; i < count; i++) {
-        float t, uu, vv;
-        if (hit_prim(prims, first + i, tr.o, tr.d, tr.tnear, tr.hit.t, t, uu, vv)) {
-            if (ANY) { tr.hit.prim = first + i; tr.hit.t = t; return true; }
-            if (t < tr.hit.t || tr.hit.prim == kNoHit) {
-                tr.hit.t = t; tr.hit.u = uu; tr.hit.v = vv; tr.hit.prim = first + i;
+// Pop the nearest unvisited child of node group tr.G, test its 8 children: the hit internal children
+// become the new tr.G (the rest of the old group is pushed), the hit leaf slots become tr.Gt.
+LJ_HD void trav_node(const DevNode8 *nodes, Trav &tr) {
+    U2 G = tr.G;
+    int bit = bfind32(G.y);
+    G.y &= ~(1u << bit);
+    if (G.y & 0xff000000u) tr.stack[tr.sp++] = G;
+    uint32_t slot = ((uint32_t)(bit - 24) ^ (tr.octinv4 & 0xffu)) & 7u;
+    uint32_t rel = (uint32_t)popc32(G.y & ~(0xffffffffu << slot) & 0xffu);
+    const DevNode8 *nd = nodes + (G.x + rel);
+    V4 q0 = ld4(&nd->q0), q1 = ld4(&nd->q1), q2 = ld4(&nd->q2), q3 = ld4(&nd->q3), q4 = ld4(&nd->q4);
+    uint32_t pk = f2u(q0.w);
+    float sx = u2f((pk & 0xffu) << 23) * tr.idir.x;
+    float sy = u2f(((pk >> 8) & 0xffu) << 23) * tr.idir.y;
+    float sz = u2f(((pk >> 16) & 0xffu) << 23) * tr.idir.z;
+    float ox = (q0.x - tr.o.x) * tr.idir.x, oy = (q0.y - tr.o.y) * tr.idir.y, oz = (q0.z - tr.o.z) * tr.idir.z;
+    // The plane distances are q * (2^e / d) + (p - o) / d: the second term carries the rounding of (p - o) and
+    // of 1/d, i.e. an absolute error of 2^-23 |(p - o)/d| that does not shrink with the distance itself.  The
+    // near planes are pulled in and the far planes pushed out by that much so the test stays conservative.
+    const float kSlabErr = 2.4e-7f;
+    float exn = fabsf(ox) * kSlabErr, eyn = fabsf(oy) * kSlabErr, ezn = fabsf(oz) * kSlabErr;
+    float oxn = ox - exn, oxf = ox + exn, oyn = oy - eyn, oyf = oy + eyn, ozn = oz - ezn, ozf = oz + ezn;
+    const float tmax_ray = tr.hit.t;
+    const bool nx = tr.d.x < 0, ny = tr.d.y < 0, nz = tr.d.z < 0;
+    uint32_t hitmask = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int half = 0; half < 2; half++) {
+        uint32_t meta4 = f2u(half ? q1.w : q1.z);
+        uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+        uint32_t inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
+        uint32_t bit_index4 = (meta4 ^ (tr.octinv4 & inner_mask4)) & 0x1f1f1f1fu;
+        uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+        uint32_t lox = f2u(half ? q2.y : q2.x), loy = f2u(half ? q2.w : q2.z), loz = f2u(half ? q3.y : q3.x);
+        uint32_t hix = f2u(half ? q3.w : q3.z), hiy = f2u(half ? q4.y : q4.x), hiz = f2u(half ? q4.w : q4.z);
+        uint32_t nearx = nx ? hix : lox, farx = nx ? lox : hix;
+        uint32_t neary = ny ? hiy : loy, fary = ny ? loy : hiy;
+        uint32_t nearz = nz ? hiz : loz, farz = nz ? loz : hiz;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int j = 0; j < 4; j++) {
+            float t0x = fmaf(byte_f(nearx, j), sx, oxn), t1x = fmaf(byte_f(farx, j), sx, oxf);
+            float t0y = fmaf(byte_f(neary, j), sy, oyn), t1y = fmaf(byte_f(fary, j), sy, oyf);
+            float t0z = fmaf(byte_f(nearz, j), sz, ozn), t1z = fmaf(byte_f(farz, j), sz, ozf);
+            float tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tr.tnear));
+            float tf = fminf(fminf(t1x, t1y), fminf(t1z, tmax_ray));
+            // conservative: widen the far side by a few ulp (Ize, "Robust BVH ray traversal")
+#if defined(LJ_BOX_ALWAYS)
+            if (true) {
+#else
+            if (tn <= tf * 1.0000008f + 1e-37f) {
+#endif
+                uint32_t cb = (child_bits4 >> (8 * j)) & 0xffu, bi = (bit_index4 >> (8 * j)) & 0xffu;
+                hitmask |= cb << bi;
             }
+        }
+    }
+    tr.G.x = f2u(q1.x);
+    tr.G.y = (hitmask & 0xff000000u) | (pk >> 24);
+    tr.Gt.x = f2u(q1.y);
+    tr.Gt.y = hitmask & 0x00ffffffu;
+}
+
+// Test ONE primitive of group tr.Gt (highest bit first).  ANY: returns true at the first hit.
+template <bool ANY>
+LJ_HD bool trav_prim(const DevPrim *prims, Trav &tr) {
+    int k = bfind32(tr.Gt.y);
+    tr.Gt.y &= ~(1u << k);
+    int idx = (int)tr.Gt.x + k;
+    float t, uu, vv;
+    if (hit_prim(prims, idx, tr.o, tr.d, tr.tnear, tr.hit.t, t, uu, vv)) {
+        if (ANY) { tr.hit.prim = idx; tr.hit.t = t; return true; }
+        if (t < tr.hit.t || tr.hit.prim == kNoHit) {
+            tr.hit.t = t; tr.hit.u = uu; tr.hit.v = vv; tr.hit.prim = idx;
         }
     }
     return false;
 }
-// Leaf step of the plain loop: test tr.node's primitives, then pop.
-template <bool ANY>
-LJ_HD bool trav_leaf(const DevPrim *prims, Trav &tr) {
-    if (trav_test_leaf<ANY>(prims, tr, tr.node)) { tr.node = kSentinel; return true; }
-    tr.node = tr.stack[--tr.sp];
-    return false;
+
+// After a node step: make tr.G the next node group to work on (pop the stack if the current one is
+// exhausted).  A popped entry may be a postponed primitive group; it then lands in tr.Gt.
+LJ_HD void trav_next_group(Trav &tr) {
+    if ((tr.G.y & 0xff000000u) == 0) {
+        tr.G.y = 0;
+        if (tr.sp > 0) {
+            U2 e = tr.stack[--tr.sp];
+            if (e.y & 0xff000000u) tr.G = e; else tr.Gt = e;
+        }
+    }
 }
+
+LJ_HD void trav_terminate(Trav &tr) { tr.G.y = 0; tr.Gt.y = 0; tr.sp = 0; }
 
 // Closest hit: the winning primitive's t is refined in fp64 (see refine_hit_t).
 LJ_HD void trav_finish_closest(const DevPrim *prims, Trav &tr) {
     if (tr.hit.prim != kNoHit) tr.hit.t = refine_hit_t(prims, tr.hit.prim, tr.o, tr.d, tr.hit.t);
 }
 
+// Plain single-ray loop (query seam S2 and shading-side helpers).
 template <bool ANY>
-LJ_HD bool trace2(const DevNode2 *nodes, const DevPrim *prims, V3 o, V3 d, float tnear, float tfar, Hit &hit) {
+LJ_HD bool trace8(const DevNode8 *nodes, const DevPrim *prims, V3 o, V3 d, float tnear, float tfar, Hit &hit) {
     Trav tr;
     trav_init(tr, o, d, tnear, tfar);
-    while (tr.node != kSentinel) {
-        if (tr.node >= 0) trav_inner(nodes, tr);
-        else if (trav_leaf<ANY>(prims, tr)) break;
+    while (!trav_done(tr)) {
+        if (tr.Gt.y == 0 && (tr.G.y & 0xff000000u)) trav_node(nodes, tr);
+        while (tr.Gt.y != 0) {
+            if (trav_prim<ANY>(prims, tr)) { trav_terminate(tr); break; }
+        }
+        trav_next_group(tr);
     }
     if (!ANY) trav_finish_closest(prims, tr);
     hit = tr.hit;

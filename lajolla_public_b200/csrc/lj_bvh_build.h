@@ -1,8 +1,11 @@
 // lj_bvh_build.h -- per-thread bodies of the GPU BVH build (replaces rtcCommitScene,
 // reference scene.cpp:20-27, and register_embree, shapes/triangle_mesh.inl:1-22, sphere.inl:151-162).
-// Stage list: primitive boxes + scene bounds -> 63-bit Morton keys -> radix sort -> Karras 2012
-// hierarchy -> bottom-up refit -> emit DevNode2/DevPrim in leaf order.  Bodies are LJ_HD so the
-// tests can run the same code serially on the host; the kernels in bvh_build.cu are thin wrappers.
+// Stage list: primitive boxes + scene bounds -> 63-bit Morton keys -> radix sort -> PLOC
+// (parallel locally-ordered clustering, Meister & Bittner 2018: bottom-up agglomeration of the
+// Morton-ordered clusters by smallest merged surface area, i.e. SAH-driven) -> top-down collapse of
+// the binary tree into 8-wide nodes with quantised child boxes (Ylitie, Karras & Laine 2017) and
+// octant-ordered child slots -> primitives rewritten in leaf order.  Bodies are LJ_HD so the tests
+// can run the same code serially on the host; the kernels in bvh_build.cu are thin wrappers.
 #pragma once
 #include "lj_scene_dev.h"
 
@@ -80,93 +83,224 @@ LJ_HD uint64_t morton63(V3 c, const Box3 &scene) {
     return (expand_bits_21(ix) << 2) | (expand_bits_21(iy) << 1) | expand_bits_21(iz);
 }
 
-LJ_HD int clz64(uint64_t x) {
-#if defined(__CUDA_ARCH__)
-    return __clzll((long long)x);
-#else
-    return x == 0 ? 64 : __builtin_clzll(x);
-#endif
-}
-LJ_HD int clz32(uint32_t x) {
-#if defined(__CUDA_ARCH__)
-    return __clz((int)x);
-#else
-    return x == 0 ? 32 : __builtin_clz(x);
-#endif
-}
+// ---- PLOC ------------------------------------------------------------------------------------
+// Binary tree under construction: node ids [0, n) are the Morton-sorted primitives, ids [n, 2n-1) are
+// internal nodes in creation order (the root is created last).
+struct Tree2 {
+    Box3 *box;    // 2n-1
+    int *left;    // 2n-1 (internal nodes only)
+    int *right;
+    int *count;   // primitives below the node
+    int n;        // number of primitives
+};
 
-// Karras 2012: common-prefix length with the index as tie breaker for duplicate keys.
-LJ_HD int karras_delta(const uint64_t *keys, int n, int i, int j) {
-    if (j < 0 || j >= n) return -1;
-    uint64_t a = keys[i], b = keys[j];
-    if (a == b) return 64 + clz32((uint32_t)i ^ (uint32_t)j);
-    return clz64(a ^ b);
-}
-
-// Internal node i of n-1: children and parent links.  child encoding here: >=0 internal, <0 leaf ~k
-// (k = position in sorted order).
-LJ_HD void karras_node(const uint64_t *keys, int n, int i, int *left, int *right, int *parent_internal, int *parent_leaf,
-                       int *range_first, int *range_count) {
-    int d = karras_delta(keys, n, i, i + 1) - karras_delta(keys, n, i, i - 1) >= 0 ? 1 : -1;
-    int dmin = karras_delta(keys, n, i, i - d);
-    int lmax = 2;
-    while (karras_delta(keys, n, i, i + lmax * d) > dmin) lmax *= 2;
-    int l = 0;
-    for (int t = lmax / 2; t >= 1; t /= 2)
-        if (karras_delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
-    int j = i + l * d;
-    int dnode = karras_delta(keys, n, i, j);
-    int s = 0;
-    int t = l;
-    do {
-        t = (t + 1) >> 1;
-        if (karras_delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
-    } while (t > 1);
-    int gamma = i + s * d + (d < 0 ? -1 : 0);
-    int lo = i < j ? i : j, hi = i < j ? j : i;
-    int lc = (lo == gamma) ? ~gamma : gamma;
-    int rc = (hi == gamma + 1) ? ~(gamma + 1) : gamma + 1;
-    left[i] = lc;
-    right[i] = rc;
-    range_first[i] = lo;          // the subtree of node i covers sorted primitives [lo, hi]
-    range_count[i] = hi - lo + 1;
-    if (lc >= 0) parent_internal[lc] = i; else parent_leaf[~lc] = i;
-    if (rc >= 0) parent_internal[rc] = i; else parent_leaf[~rc] = i;
-}
-
-// Bottom-up refit from sorted leaf k: the second thread to reach a node computes its box.
-LJ_HD void refit_from_leaf(int k, const Box3 *leaf_box, Box3 *node_box, const int *left, const int *right,
-                           const int *parent_internal, const int *parent_leaf, int *visit) {
-    int node = parent_leaf[k];
-    while (node >= 0) {
-        LJ_THREADFENCE();
-        if (LJ_ATOMIC_ADD_INT(&visit[node], 1) == 0) return;
-        LJ_THREADFENCE();
-        int lc = left[node], rc = right[node];
-        Box3 lb = lc >= 0 ? node_box[lc] : leaf_box[~lc];
-        Box3 rb = rc >= 0 ? node_box[rc] : leaf_box[~rc];
-        node_box[node] = box_union(lb, rb);
-        node = parent_internal[node];
+// Nearest neighbour of cluster slot i among slots [i-radius, i+radius]: smallest surface area of the
+// merged box; the lowest slot wins ties, which makes mutual-nearest pairs well defined.
+LJ_HD int ploc_nearest(const Tree2 &t, const int *cluster, int m, int i, int radius) {
+    Box3 bi = t.box[cluster[i]];
+    int lo = i - radius < 0 ? 0 : i - radius;
+    int hi = i + radius > m - 1 ? m - 1 : i + radius;
+    float best = LJ_INF;
+    int bj = -1;
+    for (int j = lo; j <= hi; j++) {
+        if (j == i) continue;
+        float a = box_half_area(box_union(bi, t.box[cluster[j]]));
+        if (a < best || bj < 0) { best = a; bj = j; }
     }
+    return bj;
 }
 
-// Emit the traversal node of internal node i (children's boxes stored in the parent).  A child
-// subtree holding at most max_leaf primitives is collapsed into one leaf: Karras subtrees cover a
-// contiguous range of the sorted primitive array, so the leaf is just (first, count).
-LJ_HD int leaf_ref(int first, int count) { return ~((first << 3) | (count - 1)); }
-LJ_HD DevNode2 emit_node2(int i, const Box3 *leaf_box, const Box3 *node_box, const int *left, const int *right,
-                          const int *range_first, const int *range_count, int max_leaf) {
-    int lc = left[i], rc = right[i];
-    Box3 lb = lc >= 0 ? node_box[lc] : leaf_box[~lc];
-    Box3 rb = rc >= 0 ? node_box[rc] : leaf_box[~rc];
-    int c0 = lc >= 0 ? (range_count[lc] <= max_leaf ? leaf_ref(range_first[lc], range_count[lc]) : lc) : leaf_ref(~lc, 1);
-    int c1 = rc >= 0 ? (range_count[rc] <= max_leaf ? leaf_ref(range_first[rc], range_count[rc]) : rc) : leaf_ref(~rc, 1);
-    DevNode2 nd;
-    nd.n0 = mk4(lb.lo.x, lb.hi.x, lb.lo.y, lb.hi.y);
-    nd.n1 = mk4(rb.lo.x, rb.hi.x, rb.lo.y, rb.hi.y);
-    nd.n2 = mk4(lb.lo.z, lb.hi.z, rb.lo.z, rb.hi.z);
-    nd.n3 = mk4(u2f((uint32_t)c0), u2f((uint32_t)c1), 0.f, 0.f);
-    return nd;
+// Merge step for slot i: mutual nearest neighbours become one new internal node, kept in the lower slot.
+// Returns 1 if slot i survives into the next round.
+LJ_HD int ploc_merge(const Tree2 &t, const int *cluster, const int *nearest, int i, int *next_node, int *cluster_out) {
+    int j = nearest[i];
+    if (j >= 0 && nearest[j] == i) {
+        if (i > j) return 0;
+        int a = cluster[i], b = cluster[j];
+        int id = LJ_ATOMIC_ADD_INT(next_node, 1);
+        t.left[id] = a;
+        t.right[id] = b;
+        t.box[id] = box_union(t.box[a], t.box[b]);
+        t.count[id] = t.count[a] + t.count[b];
+        cluster_out[i] = id;
+        return 1;
+    }
+    cluster_out[i] = cluster[i];
+    return 1;
+}
+
+// ---- collapse to 8-wide compressed nodes ------------------------------------------------------
+constexpr int kMaxLeafPrims = 3;      // primitives per leaf slot (unary count in 3 meta bits)
+constexpr int kBvh8StackLimit = 30;   // traversal stack entries available above the sentinel (lj_bvh.h)
+
+struct CollapseItem { int node2, node8, depth, _pad; };
+
+struct CollapseCtx {
+    Tree2 tree;
+    const DevPrim *prims_sorted;  // Morton order (tree leaf ids)
+    DevPrim *prims_out;           // final leaf order
+    DevNode8 *nodes8;
+    int *counters;                // [0] next node8, [1] next prim, [2] max depth, [3] items queued for the next level
+    CollapseItem *queue_out;
+};
+
+LJ_HD bool tree_is_leaf_slot(const Tree2 &t, int id) { return id < t.n || t.count[id] <= kMaxLeafPrims; }
+
+// primitives below a node holding at most kMaxLeafPrims of them
+LJ_HD int tree_gather_prims(const Tree2 &t, int id, int *out) {
+    int stack[4], sp = 0, k = 0;
+    stack[sp++] = id;
+    while (sp > 0) {
+        int x = stack[--sp];
+        if (x < t.n) { if (k < kMaxLeafPrims) out[k++] = x; }
+        else { stack[sp++] = t.right[x]; if (sp < 4) stack[sp++] = t.left[x]; }
+    }
+    return k;
+}
+
+LJ_HD float exp2_from_biased(int e) { return u2f((uint32_t)e << 23); }
+LJ_HD uint32_t pack4(const uint32_t *v) { return v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24); }
+
+// Smallest power-of-two step 2^e (biased exponent returned) with 255 steps covering `extent`.
+LJ_HD int quant_exponent(float extent) {
+    if (!(extent > 0)) return 1;  // any step: every quantised coordinate is 0
+    uint32_t bits = f2u(extent / 255.f);
+    int e = (int)((bits >> 23) & 0xff);
+    if (bits & 0x7fffffu) e += 1;  // round the step up to a power of two
+    if (e < 1) e = 1;
+    if (e > 254) e = 254;
+    while (e < 254 && exp2_from_biased(e) * 255.f < extent) e++;
+    return e;
+}
+
+// One wide node: gather up to 8 children from the binary tree (greedy: always open the child with the
+// largest surface area), give them octant-ordered slots, quantise their boxes, allocate their nodes /
+// primitives, and queue the internal children for the next level.
+LJ_HD void collapse_node(const CollapseCtx &c, const CollapseItem &it) {
+    const Tree2 &t = c.tree;
+    int ch[8], nch = 0;
+    if (it.node2 < t.n) {
+        ch[nch++] = it.node2;  // single-primitive scene
+    } else {
+        ch[nch++] = t.left[it.node2];
+        ch[nch++] = t.right[it.node2];
+    }
+    // phase 1 opens nodes that must stay internal (more than kMaxLeafPrims primitives below); phase 2
+    // spends the remaining slots on opening small subtrees so that leaf boxes are as tight as possible.
+    for (int phase = 0; phase < 2; phase++) {
+        while (nch < 8) {
+            int best = -1;
+            float best_area = -1;
+            for (int k = 0; k < nch; k++) {
+                int id = ch[k];
+                bool openable = phase == 0 ? !tree_is_leaf_slot(t, id) : id >= t.n;
+                if (!openable) continue;
+                float a = box_half_area(t.box[id]);
+                if (a > best_area) { best_area = a; best = k; }
+            }
+            if (best < 0) break;
+            int id = ch[best];
+            ch[best] = t.left[id];
+            ch[nch++] = t.right[id];
+        }
+    }
+    Box3 nb = box_empty();
+    for (int k = 0; k < nch; k++) nb = box_union(nb, t.box[ch[k]]);
+    // ---- slots: slot s "points" along (s&1 ? +x : -x, s&2 ? +y : -y, s&4 ? +z : -z); a ray with
+    // sign octant o visits slot (o ^ 7 ^ priority) in decreasing priority (lj_bvh.h), so the child lying
+    // furthest against the slot direction of o is entered first.  Greedy assignment by projected offset.
+    V3 cen = (nb.lo + nb.hi) * 0.5f;
+    float cost[8][8];
+    for (int k = 0; k < nch; k++) {
+        V3 d = (t.box[ch[k]].lo + t.box[ch[k]].hi) * 0.5f - cen;
+        for (int s = 0; s < 8; s++)
+            cost[k][s] = ((s & 1) ? d.x : -d.x) + ((s & 2) ? d.y : -d.y) + ((s & 4) ? d.z : -d.z);
+    }
+    int slot_child[8];
+    bool child_done[8];
+    for (int s = 0; s < 8; s++) { slot_child[s] = -1; child_done[s] = false; }
+    for (int iter = 0; iter < nch; iter++) {
+        int bk = -1, bs = -1;
+        float bc = -LJ_INF;
+        for (int k = 0; k < nch; k++) {
+            if (child_done[k]) continue;
+            for (int s = 0; s < 8; s++) {
+                if (slot_child[s] >= 0) continue;
+                if (bk < 0 || cost[k][s] > bc) { bc = cost[k][s]; bk = k; bs = s; }
+            }
+        }
+        slot_child[bs] = bk;
+        child_done[bk] = true;
+    }
+    // ---- allocation
+    uint32_t imask = 0;
+    int n_inner = 0, n_prims = 0;
+    int leaf_prims[8][kMaxLeafPrims], leaf_count[8];
+    for (int s = 0; s < 8; s++) {
+        leaf_count[s] = 0;
+        if (slot_child[s] < 0) continue;
+        int id = ch[slot_child[s]];
+        if (tree_is_leaf_slot(t, id)) {
+            leaf_count[s] = tree_gather_prims(t, id, leaf_prims[s]);
+            n_prims += leaf_count[s];
+        } else {
+            imask |= 1u << s;
+            n_inner++;
+        }
+    }
+    int child_base = n_inner ? LJ_ATOMIC_ADD_INT(&c.counters[0], n_inner) : 0;
+    int prim_base = n_prims ? LJ_ATOMIC_ADD_INT(&c.counters[1], n_prims) : 0;
+    int queue_base = n_inner ? LJ_ATOMIC_ADD_INT(&c.counters[3], n_inner) : 0;
+    // ---- quantisation frame
+    int e[3];
+    float step[3];
+    const float lo3[3] = {nb.lo.x, nb.lo.y, nb.lo.z}, hi3[3] = {nb.hi.x, nb.hi.y, nb.hi.z};
+    for (int a = 0; a < 3; a++) { e[a] = quant_exponent(hi3[a] - lo3[a]); step[a] = exp2_from_biased(e[a]); }
+    uint32_t meta[8], qlo[3][8], qhi[3][8];
+    int inner_rank = 0, prim_rel = 0;
+    for (int s = 0; s < 8; s++) {
+        meta[s] = 0;
+        for (int a = 0; a < 3; a++) { qlo[a][s] = 255; qhi[a][s] = 0; }  // empty slot: inverted box
+        if (slot_child[s] < 0) continue;
+        int id = ch[slot_child[s]];
+        const Box3 &b = t.box[id];
+        const float blo[3] = {b.lo.x, b.lo.y, b.lo.z}, bhi[3] = {b.hi.x, b.hi.y, b.hi.z};
+        for (int a = 0; a < 3; a++) {
+            int l = (int)floorf((blo[a] - lo3[a]) / step[a]);
+            int h = (int)ceilf((bhi[a] - lo3[a]) / step[a]);
+            l = clampi(l, 0, 255);
+            h = clampi(h, 0, 255);
+            // conservative under the decode lo3 + q * step evaluated in fp32
+            while (l > 0 && lo3[a] + (float)l * step[a] > blo[a]) l--;
+            while (h < 255 && lo3[a] + (float)h * step[a] < bhi[a]) h++;
+            qlo[a][s] = (uint32_t)l;
+            qhi[a][s] = (uint32_t)h;
+        }
+        if (imask & (1u << s)) {
+            meta[s] = (1u << 5) | (24u + (uint32_t)s);
+            CollapseItem q;
+            q.node2 = id; q.node8 = child_base + inner_rank; q.depth = it.depth + 1; q._pad = 0;
+            c.queue_out[queue_base + inner_rank] = q;
+            inner_rank++;
+        } else {
+            int cnt = leaf_count[s];
+            meta[s] = (((1u << cnt) - 1u) << 5) | (uint32_t)prim_rel;
+            for (int k = 0; k < cnt; k++) c.prims_out[prim_base + prim_rel + k] = c.prims_sorted[leaf_prims[s][k]];
+            prim_rel += cnt;
+        }
+    }
+    DevNode8 nd;
+    nd.q0 = mk4(nb.lo.x, nb.lo.y, nb.lo.z, u2f((uint32_t)e[0] | ((uint32_t)e[1] << 8) | ((uint32_t)e[2] << 16) | (imask << 24)));
+    nd.q1 = mk4(u2f((uint32_t)child_base), u2f((uint32_t)prim_base), u2f(pack4(meta)), u2f(pack4(meta + 4)));
+    nd.q2 = mk4(u2f(pack4(qlo[0])), u2f(pack4(qlo[0] + 4)), u2f(pack4(qlo[1])), u2f(pack4(qlo[1] + 4)));
+    nd.q3 = mk4(u2f(pack4(qlo[2])), u2f(pack4(qlo[2] + 4)), u2f(pack4(qhi[0])), u2f(pack4(qhi[0] + 4)));
+    nd.q4 = mk4(u2f(pack4(qhi[1])), u2f(pack4(qhi[1] + 4)), u2f(pack4(qhi[2])), u2f(pack4(qhi[2] + 4)));
+    c.nodes8[it.node8] = nd;
+#if defined(__CUDA_ARCH__)
+    atomicMax(&c.counters[2], it.depth);
+#else
+    if (it.depth > c.counters[2]) c.counters[2] = it.depth;
+#endif
 }
 
 }  // namespace lj

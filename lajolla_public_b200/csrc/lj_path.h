@@ -47,7 +47,7 @@ struct PathState {
 };
 
 struct RenderParams {
-    uint32_t spp_total;     // stream id = pixel * spp_total + sample
+    uint32_t spp_total;     // stream = path_stream(pixel * spp_total + sample)
     uint32_t sample_begin, sample_end;
     uint64_t seed;
     int width, height;
@@ -58,13 +58,13 @@ struct ShadeCounters { uint32_t bounces, shadow_rays, extend_rays, finished; };
 LJ_HD Pcg path_rng(const PathState &s, const RenderParams &rp) {
     Pcg r;
     r.state = s.rng_state;
-    r.inc = pcg_inc((uint64_t)s.pixel * rp.spp_total + s.sample);
+    r.inc = pcg_inc(path_stream((uint64_t)s.pixel * rp.spp_total + s.sample));
     return r;
 }
 
 // path_tracing.h:10-14 + state init (:44-53)
 LJ_HD void generate_path(const DevScene &sc, const RenderParams &rp, uint32_t pixel, uint32_t sample, PathState &s) {
-    Pcg rng = pcg_init((uint64_t)pixel * rp.spp_total + sample, rp.seed);
+    Pcg rng = pcg_init(path_stream((uint64_t)pixel * rp.spp_total + sample), rp.seed);
     int x = pixel % rp.width, y = pixel / rp.width;
     float u0 = pcg_uniform(rng), u1 = pcg_uniform(rng);
     sample_primary_pixel(sc.camera, x, y, mk2(u0, u1), s.o, s.d);

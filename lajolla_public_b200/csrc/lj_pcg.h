@@ -1,7 +1,9 @@
 // lj_pcg.h -- PCG32 XSH-RR, bit-exact restatement of the reference's pcg.h:16-68 (integer path),
 // plus the fp32 uniform the device path draws (pcg.h:49-57, the float overload).
-// One stream per camera path: stream id = pixel * spp + sample, so only the 64-bit
-// state is kept in the path record; the increment is rebuilt from the ids.
+// One stream per camera path, selected by path_stream(pixel * spp + sample): only the 64-bit state is
+// kept in the path record, the increment is rebuilt from the ids.  The path index goes through a 64-bit
+// finaliser first: PCG streams whose increments differ in a few low bits are affinely related, and the
+// samples of one pixel would otherwise sit on neighbouring streams.
 #pragma once
 #include "lj_common.h"
 
@@ -21,6 +23,14 @@ LJ_HD uint32_t pcg_next(Pcg &r) {
 }
 
 LJ_HD uint64_t pcg_inc(uint64_t stream_id) { return (stream_id << 1u) | 1u; }
+
+// splitmix64 finaliser (Steele, Lea & Flood 2014): bijective on 64 bits
+LJ_HD uint64_t path_stream(uint64_t path_index) {
+    uint64_t z = path_index + 0x9e3779b97f4a7c15ULL;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+    return z ^ (z >> 31);
+}
 
 LJ_HD Pcg pcg_init(uint64_t stream_id, uint64_t seed) {
     Pcg s;

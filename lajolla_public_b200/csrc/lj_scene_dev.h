@@ -53,18 +53,16 @@ struct DevShape {
 //   sphere:   a = (center.xyz, r) b = unused           c = (0,   bits(shape_id), bits(0),       bits(1))
 struct DevPrim { V4 a, b, c; };
 
-// Binary node, 64 B = 4 x 16-byte loads (both children's boxes live in the parent):
-//   n0 = (c0.lo.x, c0.hi.x, c0.lo.y, c0.hi.y)  n1 = (c1.lo.x, c1.hi.x, c1.lo.y, c1.hi.y)
-//   n2 = (c0.lo.z, c0.hi.z, c1.lo.z, c1.hi.z)  n3 = bits(child0, child1, 0, 0)
-// child >= 0: inner node index.  child < 0: leaf, v = ~child, first prim = v >> 3, count = (v & 7) + 1.
-struct DevNode2 { V4 n0, n1, n2, n3; };
-
 // 8-wide compressed node, 80 B = 5 x 16-byte loads (Ylitie, Karras, Laine 2017 layout):
 //   q0 = (origin.xyz, bits(ex | ey<<8 | ez<<16 | imask<<24))
 //   q1 = bits(child_base, prim_base, meta[0..3], meta[4..7])
 //   q2 = bits(qlo_x[0..3], qlo_x[4..7], qlo_y[0..3], qlo_y[4..7])
 //   q3 = bits(qlo_z[0..3], qlo_z[4..7], qhi_x[0..3], qhi_x[4..7])
 //   q4 = bits(qhi_y[0..3], qhi_y[4..7], qhi_z[0..3], qhi_z[4..7])
+// Child box k = origin + q * 2^(e - 127) per axis.  meta[k]: 0 = empty slot; internal child = 0b001 in the
+// top 3 bits and 24 + k below; leaf slot = primitive count in unary (1, 3, 7) in the top 3 bits and the index
+// of its first primitive relative to prim_base below.  Internal children are stored contiguously from
+// child_base in slot order (imask marks their slots), leaf primitives contiguously from prim_base.
 struct DevNode8 { V4 q0, q1, q2, q3, q4; };
 
 // ---- lights (light.h:14-27) --------------------------------------------------------------------
@@ -131,10 +129,8 @@ struct DevScene {
     int num_shapes;
     // BVH
     const DevPrim *prims;
-    const DevNode2 *nodes2;
-    const DevNode8 *nodes8;
+    const DevNode8 *nodes8;  // root = node 0
     int num_prims;
-    int root_is_leaf;  // degenerate scenes (1 primitive): nodes2[0] has a single leaf child
     // shading tables
     const DevMaterial *materials;
     int num_materials;

@@ -324,14 +324,16 @@ extern "C" int lj_scene_create(const lj_scene_desc *desc, lj_scene **out) {
     BvhResult bvh;
     auto t_bvh0 = std::chrono::steady_clock::now();
     {
-        cudaError_t e = build_bvh2(sc, d_prim_shape, d_prim_local, n_prims, s->stream, &bvh);
+        cudaError_t e = build_bvh8(sc, d_prim_shape, d_prim_local, n_prims, s->stream, &bvh);
         if (e != cudaSuccess) { int r = cuda_fail(e, "BVH build"); lj_scene_destroy(s); return r; }
     }
     auto t_bvh1 = std::chrono::steady_clock::now();
     s->allocations.push_back(bvh.nodes);
     s->allocations.push_back(bvh.prims);
-    s->info.device_bytes += (int64_t)bvh.num_nodes * sizeof(DevNode2) + (int64_t)n_prims * sizeof(DevPrim);
-    sc.nodes2 = bvh.nodes;
+    s->info.device_bytes += (int64_t)bvh.num_nodes * sizeof(DevNode8) + (int64_t)n_prims * sizeof(DevPrim);
+    if (bvh.num_prims_placed != n_prims) return fail(LJ_ERR_CUDA, "BVH collapse lost primitives");
+    if (bvh.depth > kBvh8StackLimit) return fail(LJ_ERR_UNSUPPORTED, "BVH deeper than the traversal stack");
+    sc.nodes8 = bvh.nodes;
     sc.prims = bvh.prims;
     sc.num_prims = n_prims;
 
@@ -460,7 +462,8 @@ extern "C" int lj_scene_create(const lj_scene_desc *desc, lj_scene **out) {
     s->info.num_triangles = n_tris;
     s->info.num_spheres = n_spheres;
     s->info.num_bvh_nodes = bvh.num_nodes;
-    s->info.bvh_width = 2;
+    s->info.bvh_width = 8;
+    s->info.bvh_depth = bvh.depth;
     s->info.bvh_build_ms = ms(t_bvh0, t_bvh1);
     s->info.prep_ms = ms(t_prep0, t_bvh0);
     s->info.upload_ms = ms(t_start, t_end) - s->info.bvh_build_ms - s->info.prep_ms;

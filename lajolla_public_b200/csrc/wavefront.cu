@@ -103,12 +103,14 @@ __global__ void __launch_bounds__(256) k_regen(const LJ_GRID_CONSTANT DevScene s
 // K2 / K3: persistent-thread traversal over the path pool.  Each warp takes 32 consecutive slots at a
 // time from a global cursor (one atomic per warp); lanes whose slot carries no ray of this kind, or
 // whose ray is finished, are refilled from the cursor once fewer than kRefillThreshold lanes of the
-// warp are still traversing.  Traversal is the speculative while-while scheme of Aila & Laine: a lane
-// that reaches a leaf postpones it and keeps descending until every active lane holds a leaf, so
-// primitive tests run with most of the warp active (the first profile showed the leaf code at 2 of
-// 32 lanes).  SHADOW = false: closest hit of pool.ray -> pool.hit.  SHADOW = true: any hit of the
-// NEE segment; an unoccluded segment adds its contribution to pool.rad.
+// warp are still traversing.  The work loop is warp-synchronous (full-mask ballots at the top of every
+// iteration), so the lanes reconverge once per step: one iteration = one wide-node step for the lanes
+// that need one, then the primitive tests the step produced.  When only a few lanes hold primitives
+// they are postponed (pushed as a group) so the tests run with more of the warp active.
+// SHADOW = false: closest hit of pool.ray -> pool.hit.  SHADOW = true: any hit of the NEE segment; an
+// unoccluded segment adds its contribution to pool.rad.
 constexpr int kRefillThreshold = 20;
+constexpr int kPrimMinLanes = 6;
 
 template <bool SHADOW>
 __global__ void __launch_bounds__(128) k_trace(const LJ_GRID_CONSTANT DevScene sc, const LJ_GRID_CONSTANT WaveArgs a) {
@@ -116,8 +118,7 @@ __global__ void __launch_bounds__(128) k_trace(const LJ_GRID_CONSTANT DevScene s
     unsigned int *cursor = &a.cursors[SHADOW ? 1 : 0];
     const int lane = LJ_LANE();
     Trav tr;
-    tr.node = kSentinel;
-    tr.leaf = 0;
+    trav_terminate(tr);
     int slot = -1;
     bool has_ray = false;
     bool drained = false;  // warp-uniform: the cursor ran past the pool
@@ -161,35 +162,38 @@ __global__ void __launch_bounds__(128) k_trace(const LJ_GRID_CONSTANT DevScene s
             if (drained) break;  // pool exhausted and every lane finished
             continue;            // this batch of slots held no rays: fetch again
         }
-        if (has_ray) {
-            while (tr.node != kSentinel || tr.leaf != 0) {
-                // inner phase: descend, postponing the first leaf, until every active lane holds one
-                while (tr.node >= 0 && tr.node != kSentinel) {
-                    trav_inner(sc.nodes2, tr);
-                    if (tr.node < 0 && tr.leaf == 0) { tr.leaf = tr.node; tr.node = tr.stack[--tr.sp]; }
-                    if (!__any_sync(__activemask(), tr.leaf == 0)) break;
-                }
-                // leaf phase
-                while (tr.leaf != 0) {
-                    bool stop = trav_test_leaf<SHADOW>(sc.prims, tr, tr.leaf);
-                    tr.leaf = 0;
-                    if (stop) { tr.node = kSentinel; break; }
-                    if (tr.node < 0) { tr.leaf = tr.node; tr.node = tr.stack[--tr.sp]; }
-                }
-                if (!drained && __popc(__activemask()) < kRefillThreshold) break;
+        // ---- work loop
+        for (;;) {
+            bool work = has_ray && !trav_done(tr);
+            if (__ballot_sync(0xffffffffu, work) == 0) break;
+            if (work && tr.Gt.y == 0 && (tr.G.y & 0xff000000u)) trav_node(sc.nodes8, tr);
+            bool prim = work && tr.Gt.y != 0;
+            unsigned pm = __ballot_sync(0xffffffffu, prim);
+            if (prim && __popc(pm) < kPrimMinLanes && (tr.G.y & 0xff000000u) && tr.sp < kTriPostponeMax) {
+                tr.stack[tr.sp++] = tr.Gt;  // postpone: keep descending, test these later
+                tr.Gt.y = 0;
+                prim = false;
             }
-            if (tr.node == kSentinel && tr.leaf == 0) {
-                if (SHADOW) {
-                    if (tr.hit.prim == kNoHit) {
-                        V4 r = a.pool.rad[slot], c = a.pool.sh_c[slot];
-                        a.pool.rad[slot] = mk4(r.x + c.x, r.y + c.y, r.z + c.z, r.w);
-                    }
-                } else {
-                    trav_finish_closest(sc.prims, tr);
-                    a.pool.hit[slot] = mk4(tr.hit.t, tr.hit.u, tr.hit.v, u2f((uint32_t)tr.hit.prim));
+            if (prim) {
+                while (tr.Gt.y != 0) {
+                    if (trav_prim<SHADOW>(sc.prims, tr)) { trav_terminate(tr); break; }
                 }
-                has_ray = false;
             }
+            if (work && tr.Gt.y == 0) trav_next_group(tr);
+            // refill once too few lanes are still traversing (every pass makes progress before it may leave)
+            if (!drained && __popc(__ballot_sync(0xffffffffu, has_ray && !trav_done(tr))) < kRefillThreshold) break;
+        }
+        if (has_ray && trav_done(tr)) {
+            if (SHADOW) {
+                if (tr.hit.prim == kNoHit) {
+                    V4 r = a.pool.rad[slot], c = a.pool.sh_c[slot];
+                    a.pool.rad[slot] = mk4(r.x + c.x, r.y + c.y, r.z + c.z, r.w);
+                }
+            } else {
+                trav_finish_closest(sc.prims, tr);
+                a.pool.hit[slot] = mk4(tr.hit.t, tr.hit.u, tr.hit.v, u2f((uint32_t)tr.hit.prim));
+            }
+            has_ray = false;
         }
     }
     warp_add(&a.counters[SHADOW ? C_SHADOW : C_CLOSEST], traced);

@@ -39,7 +39,7 @@ struct float4 { float x, y, z, w; };
 typedef int cudaError_t;
 typedef void *cudaStream_t;
 typedef std::chrono::steady_clock::time_point *cudaEvent_t;
-enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2 };
+enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorUnknown = 999 };
 enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
 
 inline const char *cudaGetErrorString(cudaError_t) { return "hostsim error"; }

@@ -249,12 +249,24 @@ def check_scene_info(scene, ref):
     assert abs(i.shadow_epsilon - r["eps"]) <= 1e-6 * r["eps"]
 
 
-def image_stats(img, ref_img, var=None, ref_var=None):
-    """relMSE and, when both variance-of-the-mean buffers exist, the per-pixel z statistic."""
-    d = img.astype(np.float64) - ref_img
-    out = dict(relmse=float(np.mean(d ** 2 / (ref_img.astype(np.float64) ** 2 + 1e-2))),
-               mean=img.mean(axis=(0, 1)).tolist(), ref_mean=ref_img.mean(axis=(0, 1)).tolist())
+def image_stats(img, ref_img, var=None, ref_var=None, block=8):
+    """relMSE and, when both variance-of-the-mean buffers exist, two z statistics of img - ref_img:
+    per pixel channel (|z| > 3 fraction) and per `block` x `block` tile mean (|z| > 4 fraction; averaging 64
+    pixels brings the heavy-tailed light-transport noise close to Gaussian, so this one detects small biases).
+    A floor of (1e-4 * value)^2 on the variance keeps constant pixels (directly visible emitters) from turning
+    fp32-vs-fp64 round-off into infinite z."""
+    a = img.astype(np.float64)
+    b = ref_img.astype(np.float64)
+    d = a - b
+    out = dict(relmse=float(np.mean(d ** 2 / (b ** 2 + 1e-2))), mean=a.mean(axis=(0, 1)).tolist(), ref_mean=b.mean(axis=(0, 1)).tolist())
     if var is not None and ref_var is not None:
-        z = d / np.sqrt(np.maximum(var + ref_var, 1e-20))
+        v = var.astype(np.float64) + ref_var.astype(np.float64) + (1e-4 * np.maximum(np.abs(a), np.abs(b))) ** 2 + 1e-20
+        z = d / np.sqrt(v)
         out["frac_z_gt_3"] = float((np.abs(z) > 3).mean())
+        h, w = (a.shape[0] // block) * block, (a.shape[1] // block) * block
+        db = d[:h, :w].reshape(h // block, block, w // block, block, 3).mean(axis=(1, 3))
+        vb = v[:h, :w].reshape(h // block, block, w // block, block, 3).sum(axis=(1, 3)) / block ** 4
+        zb = db / np.sqrt(vb)
+        out["block_frac_z_gt_4"] = float((np.abs(zb) > 4).mean())
+        out["block_z_rms"] = float(np.sqrt(np.mean(np.clip(zb, -6, 6) ** 2)))  # clipped: one zero-variance tile must not decide
     return out

@@ -90,31 +90,43 @@ def test_texture_and_mip_parity(oracle):
             assert a.shape == b.shape and np.abs(a - b).max() < 1e-6
 
 
-@pytest.mark.parametrize("name,spp,ref_spp", [("cbox", 64, 64), ("veach_mi", 256, 128), ("sponza", 64, 16)])
-def test_image_parity(oracle, name, spp, ref_spp):
-    """Parity test 3 of north_star: converged-image agreement with the reference's own CPU render().
-    Bounds: per-channel image mean within 1 %; per-pixel two-sample z statistic built from the device's
-    per-pixel sample variance (both renders draw from the same estimator, so var_ref = var_gpu * spp/ref_spp):
-    at most 1.5 % of pixel channels beyond |z| > 3 (heavy-tailed light-transport noise sits above the Gaussian
-    0.27 %); relMSE below the Monte Carlo noise floor at these spp for the two low-variance scenes
-    (0.05 cbox, 0.1 sponza; veach_mi's specular highlights make relMSE a firefly detector, recorded only)."""
+@pytest.mark.parametrize("name,spp", [("cbox", 64), ("veach_mi", 256), ("sponza", 64)])
+def test_image_parity(oracle, name, spp):
+    """Parity test 3 of north_star: image agreement with the reference's own CPU render() at equal spp.
+    The statistical test is calibrated against its own null: the device renders the scene twice with different
+    seeds (A, B) and the z statistics of A - B (same estimator by construction) give the tail fractions that
+    Monte Carlo noise alone produces at this spp; A - reference must not exceed them by more than a small margin.
+      * per-channel image mean within 1 %
+      * fraction of pixel channels with |z| > 3:       reference <= 1.25 x null + 0.3 %
+      * fraction of 8x8 tile means with |z| > 4:       reference <= null + 0.2 %   (bias detector)
+      * rms of the tile z:                             reference <= 1.15 x null
+      * relMSE below the noise floor at these spp for the two low-variance scenes (0.05 cbox,
+        0.1 sponza; veach_mi's specular highlights make relMSE a firefly detector, recorded only).
+    The reference keeps no per-pixel variance; both renders draw from the same estimator, so var_ref = var_gpu is
+    used -- in the null too (B's own variance is ignored), because a rare bright sample inflates the variance
+    estimate of the render it falls in and the two statistics must be blind to it in the same way."""
     sc, ref = pair(oracle, name)
     img, var = sc.render(spp=spp, variance=True)
     st = sc.last_stats
+    img_b, var_b = sc.render(spp=spp, variance=True, seed=0x5eed5eed5eed)
     h, w = img.shape[:2]
     assert st.samples == w * h * spp
-    ref_img, secs = ref.render(spp=ref_spp)
-    s = pc.image_stats(img, ref_img, var, var * (spp / ref_spp))
+    ref_img, secs = ref.render(spp=spp)
+    null = pc.image_stats(img_b, img, var, var)  # B plays the reference: same rule, var of A on both sides
+    s = pc.image_stats(img, ref_img, var, var)
     bound = {"cbox": 0.05, "veach_mi": float("inf"), "sponza": 0.1}[name]
-    record("image_parity", dict(scene=name, spp=spp, ref_spp=ref_spp, gpu_ms=st.render_ms, ref_s=secs, **s,
-                                gpu_msamples=st.samples / st.render_ms / 1e3, ref_msamples=w * h * ref_spp / secs / 1e6,
+    record("image_parity", dict(scene=name, spp=spp, gpu_ms=st.render_ms, ref_s=secs, **s,
+                                null={k: null[k] for k in ("relmse", "frac_z_gt_3", "block_frac_z_gt_4", "block_z_rms")},
+                                gpu_msamples=st.samples / st.render_ms / 1e3, ref_msamples=w * h * spp / secs / 1e6,
                                 rays=st.closest_rays + st.shadow_rays, bounces=st.bounces, waves=st.waves))
     np.save(os.path.join(OUT, f"img_{name}_gpu.npy"), img.astype(np.float16))
     np.save(os.path.join(OUT, f"img_{name}_ref.npy"), ref_img.astype(np.float16))
     assert np.all(np.isfinite(img))
     assert np.allclose(s["mean"], s["ref_mean"], rtol=0.01), s
     assert s["relmse"] < bound, s
-    assert s["frac_z_gt_3"] < 0.015, s
+    assert s["frac_z_gt_3"] <= 1.25 * null["frac_z_gt_3"] + 0.003, (s, null)
+    assert s["block_frac_z_gt_4"] <= null["block_frac_z_gt_4"] + 0.002, (s, null)
+    assert s["block_z_rms"] <= 1.15 * null["block_z_rms"], (s, null)
 
 
 def test_sample_range_split_is_additive(oracle):
