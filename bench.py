@@ -44,40 +44,54 @@ def load_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi SM clocks + throttle reasons while the timed region runs."""
-
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clocks + throttle reasons through NVML while the timed region runs (in-process: forking
+    nvidia-smi from a process that holds a CUDA context stalls the thread that is queueing kernels)."""
 
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
         self.gpu = gpu_index
         self.rows = []
         self.stop_flag = threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            ids = [int(x) for x in vis.split(",") if x.strip().isdigit()]
+            phys = ids[gpu_index] if gpu_index < len(ids) else gpu_index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
 
     def run(self):
+        n = self.nvml
+        if n is None:
+            return
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                self.rows.append((n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM),
+                                  n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM),
+                                  n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)))
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.5)  # NVML queries take driver locks the kernel-queueing thread also needs: keep them rare
 
     def summary(self):
         self.stop_flag.set()
-        self.join(timeout=6)
-        sm = sorted(float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit())
-        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        self.join(timeout=3)
+        n = self.nvml
+        sm = sorted(r[0] for r in self.rows)
         reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            for k, nm in enumerate(names):
-                if len(r) > 5 + k and r[5 + k].lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+        if n is not None:
+            names = {"hw_slowdown": n.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": n.nvmlClocksEventReasonHwThermalSlowdown,
+                     "sw_thermal_slowdown": n.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": n.nvmlClocksEventReasonSwPowerCap}
+            for r in self.rows:
+                for nm, bit in names.items():
+                    if r[2] & bit:
+                        reasons.add(nm)
+        return {"sm_mhz": float(sm[len(sm) // 2]) if sm else None, "sm_max_mhz": float(max(r[1] for r in self.rows)) if self.rows else None,
                 "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
@@ -192,7 +206,7 @@ def main():
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     agg = {"extend_ms": 0.0, "shadow_ms": 0.0, "shade_ms": 0.0, "regen_ms": 0.0, "render_ms": 0.0, "closest": 0, "shadow": 0,
-           "bounces": 0, "launches": 0, "extend_launches": 0, "samples": 0, "waves": 0}
+           "bounces": 0, "launches": 0, "extend_launches": 0, "samples": 0, "waves": 0, "node_steps": 0, "prim_tests": 0}
     e0.record(stream)
     for _ in range(args.steps):
         st = step()
@@ -201,6 +215,7 @@ def main():
         agg["closest"] += st.closest_rays; agg["shadow"] += st.shadow_rays; agg["bounces"] += st.bounces
         agg["launches"] += st.kernel_launches + (1 if dist is not None else 0)
         agg["extend_launches"] += st.extend_launches; agg["samples"] += st.samples; agg["waves"] += st.waves
+        agg["node_steps"] += st.node_steps; agg["prim_tests"] += st.prim_tests
     e1.record(stream)
     barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
@@ -241,6 +256,8 @@ def main():
             "mrays_per_s": (agg["closest"] + agg["shadow"]) * world / (ms_total / 1e3) / 1e6,
             "rays_per_sample": (agg["closest"] + agg["shadow"]) / max(agg["samples"], 1),
             "mean_bounces": agg["bounces"] / max(agg["samples"], 1),
+            "node_steps_per_ray": agg["node_steps"] / max(agg["closest"] + agg["shadow"], 1),
+            "prim_tests_per_ray": agg["prim_tests"] / max(agg["closest"] + agg["shadow"], 1),
             "stage_ms_per_step": {k: agg[k] / args.steps for k in ("regen_ms", "extend_ms", "shade_ms", "shadow_ms", "render_ms")},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": int(cdesc_bytes),

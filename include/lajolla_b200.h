@@ -178,6 +178,8 @@ typedef struct lj_stats {
     uint64_t kernel_launches;  /* kernels launched by this call */
     uint64_t waves;
     uint64_t extend_launches, shadow_launches, shade_launches, regen_launches;
+    uint64_t node_steps;       /* wide-node tests executed by both traversal kernels */
+    uint64_t prim_tests;       /* ray/primitive tests executed by both traversal kernels */
 } lj_stats;
 
 /* Selects the CUDA device for the calling thread; LJ_ERR_NO_DEVICE if there is none. */

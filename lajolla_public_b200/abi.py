@@ -79,7 +79,8 @@ class lj_stats(C.Structure):
     _fields_ = [("render_ms", f64), ("extend_ms", f64), ("shadow_ms", f64), ("shade_ms", f64), ("regen_ms", f64),
                 ("samples", u64), ("closest_rays", u64), ("shadow_rays", u64), ("bounces", u64),
                 ("kernel_launches", u64), ("waves", u64),
-                ("extend_launches", u64), ("shadow_launches", u64), ("shade_launches", u64), ("regen_launches", u64)]
+                ("extend_launches", u64), ("shadow_launches", u64), ("shade_launches", u64), ("regen_launches", u64),
+                ("node_steps", u64), ("prim_tests", u64)]
 
 
 class lj_ray(C.Structure):

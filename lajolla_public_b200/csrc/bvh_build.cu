@@ -217,6 +217,8 @@ cudaError_t build_bvh8(const DevScene &sc, const int *d_prim_shape, const int *d
         ctx.prims_out = prims;
         ctx.nodes8 = nodes;
         ctx.counters = d_ints + 2;
+        ctx.max_leaf = kMaxLeafPrims;  // LJ_BVH_MAX_LEAF in [1, 3] for tuning runs
+        if (const char *e = getenv("LJ_BVH_MAX_LEAF")) ctx.max_leaf = atoi(e) < 1 ? 1 : (atoi(e) > kMaxLeafPrims ? kMaxLeafPrims : atoi(e));
         CollapseItem first = {root2, 0, 1, 0};
         int init[4] = {1, 0, 0, 0};
         CK(cudaMemcpyAsync(queue_a, &first, sizeof(first), cudaMemcpyHostToDevice, stream));

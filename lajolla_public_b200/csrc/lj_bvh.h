@@ -17,8 +17,17 @@ struct Hit {
 
 // Pluecker edge-function test (the formulation of Embree's ROBUST triangle intersector) in fp32.
 // The edge functions of a shared edge are exact negations of each other in the two triangles, so
-// the inclusive sign test is watertight along shared edges.
-LJ_HD bool hit_triangle(V3 A, V3 B, V3 C, V3 o, V3 d, float tnear, float tfar, float &t, float &u, float &v) {
+// the inclusive sign test is watertight along shared edges.  Traversal only needs hit / t (any t it
+// reports is re-evaluated in fp64 for the winning primitive, refine_hit_t); the barycentrics of the
+// winner are computed once at the end by triangle_uv from the same edge functions.
+LJ_HD float fast_rcp(float x) {
+#if defined(__CUDA_ARCH__)
+    return __frcp_rn(x);
+#else
+    return 1.0f / x;
+#endif
+}
+LJ_HD bool hit_triangle(V3 A, V3 B, V3 C, V3 o, V3 d, float tnear, float tfar, float &t) {
     V3 v0 = A - o, v1 = B - o, v2 = C - o;
     V3 e0 = v2 - v0, e1 = v0 - v1, e2 = v1 - v2;
     float U = dot(cross(e0, v2 + v0), d);
@@ -26,18 +35,24 @@ LJ_HD bool hit_triangle(V3 A, V3 B, V3 C, V3 o, V3 d, float tnear, float tfar, f
     float W = dot(cross(e2, v1 + v2), d);
     float mn = fminf(U, fminf(V, W)), mx = fmaxf(U, fmaxf(V, W));
     if (!(mn >= 0 || mx <= 0)) return false;
-    float UVW = U + V + W;
-    if (UVW == 0) return false;
+    if (U + V + W == 0) return false;
     V3 Ng = cross(e0, e1);
     float den = dot(Ng, d);
     if (den == 0) return false;
-    float tt = dot(v0, Ng) / den;
+    float tt = dot(v0, Ng) * fast_rcp(den);
     if (!(tt >= tnear && tt <= tfar)) return false;
     t = tt;
-    float r = 1 / UVW;
+    return true;
+}
+LJ_HD void triangle_uv(V3 A, V3 B, V3 C, V3 o, V3 d, float &u, float &v) {
+    V3 v0 = A - o, v1 = B - o, v2 = C - o;
+    V3 e0 = v2 - v0, e1 = v0 - v1, e2 = v1 - v2;
+    float U = dot(cross(e0, v2 + v0), d);
+    float V = dot(cross(e1, v0 + v1), d);
+    float W = dot(cross(e2, v1 + v2), d);
+    float r = 1 / (U + V + W);
     u = fminf(U * r, 1.0f);
     v = fminf(V * r, 1.0f);
-    return true;
 }
 
 // Ray/sphere, nearest root in [tnear, tfar) like sphere.inl:40-106.  fp32 needs a better
@@ -68,15 +83,18 @@ LJ_HD bool prim_is_sphere(const V4 &c) { return f2u(c.w) != 0; }
 LJ_HD int prim_shape_id(const V4 &c) { return (int)f2u(c.y); }
 LJ_HD int prim_primitive_id(const V4 &c) { return (int)f2u(c.z); }
 
-LJ_HD bool hit_prim(const DevPrim *prims, int i, V3 o, V3 d, float tnear, float tfar, float &t, float &u, float &v) {
+LJ_HD bool hit_prim(const DevPrim *prims, int i, V3 o, V3 d, float tnear, float tfar, float &t) {
     V4 a = ld4(&prims[i].a);
     V4 c = ld4(&prims[i].c);
-    if (prim_is_sphere(c)) {
-        u = 0; v = 0;
-        return hit_sphere(xyz(a), a.w, o, d, tnear, tfar, t);
-    }
+    if (prim_is_sphere(c)) return hit_sphere(xyz(a), a.w, o, d, tnear, tfar, t);
     V4 b = ld4(&prims[i].b);
-    return hit_triangle(xyz(a), mk3(a.w, b.x, b.y), mk3(b.z, b.w, c.x), o, d, tnear, tfar, t, u, v);
+    return hit_triangle(xyz(a), mk3(a.w, b.x, b.y), mk3(b.z, b.w, c.x), o, d, tnear, tfar, t);
+}
+// barycentrics of the final hit (spheres carry none: their (u, v) come from the hit point, lj_shapes.h)
+LJ_HD void prim_uv(const DevPrim *prims, int i, V3 o, V3 d, float &u, float &v) {
+    V4 a = ld4(&prims[i].a), b = ld4(&prims[i].b), c = ld4(&prims[i].c);
+    u = 0; v = 0;
+    if (!prim_is_sphere(c)) triangle_uv(xyz(a), mk3(a.w, b.x, b.y), mk3(b.z, b.w, c.x), o, d, u, v);
 }
 
 // Once the closest primitive is known its t is re-evaluated in fp64 on the same fp32 inputs: a grazing
@@ -144,7 +162,17 @@ LJ_HD uint32_t sign_extend_s8x4(uint32_t v) {
     return ((v >> 7) & 0x01010101u) * 0xffu;
 #endif
 }
-LJ_HD float byte_f(uint32_t v, int i) { return (float)((v >> (8 * i)) & 0xffu); }
+// 1 + q / 32768 for byte i of v: the byte is dropped into the mantissa of 1.0f with one PRMT (full-rate ALU)
+// instead of a shift, a mask and an I2F (quarter-rate conversion pipe, 48 of them per node otherwise).
+template <int I>
+LJ_HD float byte_m(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(__byte_perm(v, 0x3f800000u, 0x7604u | (I << 4)));
+#else
+    return u2f(0x3f800000u | (((v >> (8 * I)) & 0xffu) << 8));
+#endif
+}
+constexpr float kByteScale = 32768.0f;
 
 struct Trav {
     V3 o, d;
@@ -157,7 +185,9 @@ struct Trav {
     U2 stack[kStack8];
 };
 
-LJ_HD bool trav_done(const Trav &tr) { return (tr.G.y & 0xff000000u) == 0 && tr.Gt.y == 0 && tr.sp == 0; }
+// Invariant between steps (kept by trav_next_group): G.y is either 0 or carries at least one hit bit, and the
+// stack is only non-empty while G or Gt is, so "finished" is simply both groups being empty.
+LJ_HD bool trav_done(const Trav &tr) { return (tr.G.y | tr.Gt.y) == 0; }
 
 LJ_HD void trav_init(Trav &tr, V3 o, V3 d, float tnear, float tfar) {
     tr.o = o; tr.d = d;
@@ -188,16 +218,19 @@ LJ_HD void trav_node(const DevNode8 *nodes, Trav &tr) {
     const DevNode8 *nd = nodes + (G.x + rel);
     V4 q0 = ld4(&nd->q0), q1 = ld4(&nd->q1), q2 = ld4(&nd->q2), q3 = ld4(&nd->q3), q4 = ld4(&nd->q4);
     uint32_t pk = f2u(q0.w);
-    float sx = u2f((pk & 0xffu) << 23) * tr.idir.x;
-    float sy = u2f(((pk >> 8) & 0xffu) << 23) * tr.idir.y;
-    float sz = u2f(((pk >> 16) & 0xffu) << 23) * tr.idir.z;
+    // Plane distance of quantised coordinate q: q * (2^e / d) + (p - o) / d, evaluated as m * s + (a - s) with
+    // m = 1 + q / 32768 (byte_m) and s = 32768 * 2^e / d: one PRMT and one FFMA per plane.
+    float sx = u2f((pk & 0xffu) << 23) * kByteScale * tr.idir.x;
+    float sy = u2f(((pk >> 8) & 0xffu) << 23) * kByteScale * tr.idir.y;
+    float sz = u2f(((pk >> 16) & 0xffu) << 23) * kByteScale * tr.idir.z;
     float ox = (q0.x - tr.o.x) * tr.idir.x, oy = (q0.y - tr.o.y) * tr.idir.y, oz = (q0.z - tr.o.z) * tr.idir.z;
-    // The plane distances are q * (2^e / d) + (p - o) / d: the second term carries the rounding of (p - o) and
-    // of 1/d, i.e. an absolute error of 2^-23 |(p - o)/d| that does not shrink with the distance itself.  The
-    // near planes are pulled in and the far planes pushed out by that much so the test stays conservative.
+    // The addend carries the rounding of (p - o), of 1/d and of the subtraction of s: an absolute error of
+    // 2^-23 (|a| + |s|) that does not shrink with the distance itself (|s| 2^-23 is 0.4 % of one quantisation
+    // step).  Near planes are pulled in and far planes pushed out by that much so the test stays conservative.
     const float kSlabErr = 2.4e-7f;
-    float exn = fabsf(ox) * kSlabErr, eyn = fabsf(oy) * kSlabErr, ezn = fabsf(oz) * kSlabErr;
-    float oxn = ox - exn, oxf = ox + exn, oyn = oy - eyn, oyf = oy + eyn, ozn = oz - ezn, ozf = oz + ezn;
+    float exn = (fabsf(ox) + fabsf(sx)) * kSlabErr, eyn = (fabsf(oy) + fabsf(sy)) * kSlabErr, ezn = (fabsf(oz) + fabsf(sz)) * kSlabErr;
+    float oxn = (ox - sx) - exn, oxf = (ox - sx) + exn, oyn = (oy - sy) - eyn, oyf = (oy - sy) + eyn;
+    float ozn = (oz - sz) - ezn, ozf = (oz - sz) + ezn;
     const float tmax_ray = tr.hit.t;
     const bool nx = tr.d.x < 0, ny = tr.d.y < 0, nz = tr.d.z < 0;
     uint32_t hitmask = 0;
@@ -215,28 +248,24 @@ LJ_HD void trav_node(const DevNode8 *nodes, Trav &tr) {
         uint32_t nearx = nx ? hix : lox, farx = nx ? lox : hix;
         uint32_t neary = ny ? hiy : loy, fary = ny ? loy : hiy;
         uint32_t nearz = nz ? hiz : loz, farz = nz ? loz : hiz;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-        for (int j = 0; j < 4; j++) {
-            float t0x = fmaf(byte_f(nearx, j), sx, oxn), t1x = fmaf(byte_f(farx, j), sx, oxf);
-            float t0y = fmaf(byte_f(neary, j), sy, oyn), t1y = fmaf(byte_f(fary, j), sy, oyf);
-            float t0z = fmaf(byte_f(nearz, j), sz, ozn), t1z = fmaf(byte_f(farz, j), sz, ozf);
-            float tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tr.tnear));
-            float tf = fminf(fminf(t1x, t1y), fminf(t1z, tmax_ray));
-            // conservative: widen the far side by a few ulp (Ize, "Robust BVH ray traversal")
-#if defined(LJ_BOX_ALWAYS)
-            if (true) {
-#else
-            if (tn <= tf * 1.0000008f + 1e-37f) {
-#endif
-                uint32_t cb = (child_bits4 >> (8 * j)) & 0xffu, bi = (bit_index4 >> (8 * j)) & 0xffu;
-                hitmask |= cb << bi;
-            }
+#define LJ_CHILD(J)                                                                                         \
+        {                                                                                                       \
+            float t0x = fmaf(byte_m<J>(nearx), sx, oxn), t1x = fmaf(byte_m<J>(farx), sx, oxf);                  \
+            float t0y = fmaf(byte_m<J>(neary), sy, oyn), t1y = fmaf(byte_m<J>(fary), sy, oyf);                  \
+            float t0z = fmaf(byte_m<J>(nearz), sz, ozn), t1z = fmaf(byte_m<J>(farz), sz, ozf);                  \
+            float tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tr.tnear));                                            \
+            float tf = fminf(fminf(t1x, t1y), fminf(t1z, tmax_ray));                                            \
+            /* conservative: widen the far side by a few ulp (Ize, "Robust BVH ray traversal") */              \
+            if (tn <= tf * 1.0000008f + 1e-37f) {                                                               \
+                uint32_t cb = (child_bits4 >> (8 * J)) & 0xffu, bi = (bit_index4 >> (8 * J)) & 0xffu;           \
+                hitmask |= cb << bi;                                                                            \
+            }                                                                                                   \
         }
+        LJ_CHILD(0) LJ_CHILD(1) LJ_CHILD(2) LJ_CHILD(3)
+#undef LJ_CHILD
     }
     tr.G.x = f2u(q1.x);
-    tr.G.y = (hitmask & 0xff000000u) | (pk >> 24);
+    tr.G.y = (hitmask & 0xff000000u) ? ((hitmask & 0xff000000u) | (pk >> 24)) : 0u;  // keep the invariant of trav_done
     tr.Gt.x = f2u(q1.y);
     tr.Gt.y = hitmask & 0x00ffffffu;
 }
@@ -247,25 +276,20 @@ LJ_HD bool trav_prim(const DevPrim *prims, Trav &tr) {
     int k = bfind32(tr.Gt.y);
     tr.Gt.y &= ~(1u << k);
     int idx = (int)tr.Gt.x + k;
-    float t, uu, vv;
-    if (hit_prim(prims, idx, tr.o, tr.d, tr.tnear, tr.hit.t, t, uu, vv)) {
+    float t;
+    if (hit_prim(prims, idx, tr.o, tr.d, tr.tnear, tr.hit.t, t)) {
         if (ANY) { tr.hit.prim = idx; tr.hit.t = t; return true; }
-        if (t < tr.hit.t || tr.hit.prim == kNoHit) {
-            tr.hit.t = t; tr.hit.u = uu; tr.hit.v = vv; tr.hit.prim = idx;
-        }
+        if (t < tr.hit.t || tr.hit.prim == kNoHit) { tr.hit.t = t; tr.hit.prim = idx; }
     }
     return false;
 }
 
-// After a node step: make tr.G the next node group to work on (pop the stack if the current one is
-// exhausted).  A popped entry may be a postponed primitive group; it then lands in tr.Gt.
+// After a step: if both groups are used up, pop the next one.  A popped entry is either a node group or a
+// postponed primitive group (no hit bits in the top byte); the latter lands in tr.Gt.
 LJ_HD void trav_next_group(Trav &tr) {
-    if ((tr.G.y & 0xff000000u) == 0) {
-        tr.G.y = 0;
-        if (tr.sp > 0) {
-            U2 e = tr.stack[--tr.sp];
-            if (e.y & 0xff000000u) tr.G = e; else tr.Gt = e;
-        }
+    if ((tr.G.y | tr.Gt.y) == 0 && tr.sp > 0) {
+        U2 e = tr.stack[--tr.sp];
+        if (e.y & 0xff000000u) tr.G = e; else tr.Gt = e;
     }
 }
 
@@ -273,7 +297,9 @@ LJ_HD void trav_terminate(Trav &tr) { tr.G.y = 0; tr.Gt.y = 0; tr.sp = 0; }
 
 // Closest hit: the winning primitive's t is refined in fp64 (see refine_hit_t).
 LJ_HD void trav_finish_closest(const DevPrim *prims, Trav &tr) {
-    if (tr.hit.prim != kNoHit) tr.hit.t = refine_hit_t(prims, tr.hit.prim, tr.o, tr.d, tr.hit.t);
+    if (tr.hit.prim == kNoHit) return;
+    prim_uv(prims, tr.hit.prim, tr.o, tr.d, tr.hit.u, tr.hit.v);
+    tr.hit.t = refine_hit_t(prims, tr.hit.prim, tr.o, tr.d, tr.hit.t);
 }
 
 // Plain single-ray loop (query seam S2 and shading-side helpers).
@@ -282,7 +308,7 @@ LJ_HD bool trace8(const DevNode8 *nodes, const DevPrim *prims, V3 o, V3 d, float
     Trav tr;
     trav_init(tr, o, d, tnear, tfar);
     while (!trav_done(tr)) {
-        if (tr.Gt.y == 0 && (tr.G.y & 0xff000000u)) trav_node(nodes, tr);
+        if (tr.Gt.y == 0) trav_node(nodes, tr);
         while (tr.Gt.y != 0) {
             if (trav_prim<ANY>(prims, tr)) { trav_terminate(tr); break; }
         }

@@ -142,9 +142,10 @@ struct CollapseCtx {
     DevNode8 *nodes8;
     int *counters;                // [0] next node8, [1] next prim, [2] max depth, [3] items queued for the next level
     CollapseItem *queue_out;
+    int max_leaf;                 // primitives per leaf slot, 1..kMaxLeafPrims
 };
 
-LJ_HD bool tree_is_leaf_slot(const Tree2 &t, int id) { return id < t.n || t.count[id] <= kMaxLeafPrims; }
+LJ_HD bool tree_is_leaf_slot(const Tree2 &t, int id, int max_leaf) { return id < t.n || t.count[id] <= max_leaf; }
 
 // primitives below a node holding at most kMaxLeafPrims of them
 LJ_HD int tree_gather_prims(const Tree2 &t, int id, int *out) {
@@ -193,7 +194,7 @@ LJ_HD void collapse_node(const CollapseCtx &c, const CollapseItem &it) {
             float best_area = -1;
             for (int k = 0; k < nch; k++) {
                 int id = ch[k];
-                bool openable = phase == 0 ? !tree_is_leaf_slot(t, id) : id >= t.n;
+                bool openable = phase == 0 ? !tree_is_leaf_slot(t, id, c.max_leaf) : id >= t.n;
                 if (!openable) continue;
                 float a = box_half_area(t.box[id]);
                 if (a > best_area) { best_area = a; best = k; }
@@ -240,7 +241,7 @@ LJ_HD void collapse_node(const CollapseCtx &c, const CollapseItem &it) {
         leaf_count[s] = 0;
         if (slot_child[s] < 0) continue;
         int id = ch[slot_child[s]];
-        if (tree_is_leaf_slot(t, id)) {
+        if (tree_is_leaf_slot(t, id, c.max_leaf)) {
             leaf_count[s] = tree_gather_prims(t, id, leaf_prims[s]);
             n_prims += leaf_count[s];
         } else {

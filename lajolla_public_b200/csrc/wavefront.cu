@@ -12,12 +12,14 @@
 // (profiles/r01_b_*).
 #include "scene.cuh"
 
+#include <stdlib.h>
+
 #include <algorithm>
 #include <vector>
 
 namespace lj {
 
-enum { C_SAMPLES = 0, C_CLOSEST, C_SHADOW, C_BOUNCES, C_ACTIVE, C_NEXT, C_COUNT };
+enum { C_SAMPLES = 0, C_CLOSEST, C_SHADOW, C_BOUNCES, C_ACTIVE, C_NEXT, C_NODE_STEPS, C_PRIM_TESTS, C_COUNT };
 
 struct WaveArgs {
     PathPool pool;
@@ -28,6 +30,7 @@ struct WaveArgs {
     unsigned int *cursors;         // fetch cursors of the persistent trace kernels: [0] extend, [1] shadow
     unsigned long long total_items;  // padded pixels * samples in this call
     int tiles_x, tiles_y;
+    int prim_min_lanes, refill_threshold;  // scheduling policy of k_trace
 };
 
 __device__ __forceinline__ void warp_add(unsigned long long *ctr, unsigned v) {
@@ -109,8 +112,8 @@ __global__ void __launch_bounds__(256) k_regen(const LJ_GRID_CONSTANT DevScene s
 // they are postponed (pushed as a group) so the tests run with more of the warp active.
 // SHADOW = false: closest hit of pool.ray -> pool.hit.  SHADOW = true: any hit of the NEE segment; an
 // unoccluded segment adds its contribution to pool.rad.
-constexpr int kRefillThreshold = 20;
-constexpr int kPrimMinLanes = 6;
+constexpr int kRefillThreshold = 20;  // defaults; LJ_REFILL / LJ_PRIM_MIN_LANES override them for tuning runs
+constexpr int kPrimMinLanes = 12;
 
 template <bool SHADOW>
 __global__ void __launch_bounds__(128) k_trace(const LJ_GRID_CONSTANT DevScene sc, const LJ_GRID_CONSTANT WaveArgs a) {
@@ -122,7 +125,7 @@ __global__ void __launch_bounds__(128) k_trace(const LJ_GRID_CONSTANT DevScene s
     int slot = -1;
     bool has_ray = false;
     bool drained = false;  // warp-uniform: the cursor ran past the pool
-    unsigned traced = 0;
+    unsigned traced = 0, node_steps = 0, prim_tests = 0;
     for (;;) {
         // ---- fetch: lanes without a ray take the next slots
         unsigned want = drained ? 0u : __ballot_sync(0xffffffffu, !has_ray);
@@ -162,28 +165,38 @@ __global__ void __launch_bounds__(128) k_trace(const LJ_GRID_CONSTANT DevScene s
             if (drained) break;  // pool exhausted and every lane finished
             continue;            // this batch of slots held no rays: fetch again
         }
-        // ---- work loop
-        for (;;) {
-            bool work = has_ray && !trav_done(tr);
-            if (__ballot_sync(0xffffffffu, work) == 0) break;
-            if (work && tr.Gt.y == 0 && (tr.G.y & 0xff000000u)) trav_node(sc.nodes8, tr);
-            bool prim = work && tr.Gt.y != 0;
-            unsigned pm = __ballot_sync(0xffffffffu, prim);
-            if (prim && __popc(pm) < kPrimMinLanes && (tr.G.y & 0xff000000u) && tr.sp < kTriPostponeMax) {
-                tr.stack[tr.sp++] = tr.Gt;  // postpone: keep descending, test these later
-                tr.Gt.y = 0;
-                prim = false;
-            }
-            if (prim) {
-                while (tr.Gt.y != 0) {
-                    if (trav_prim<SHADOW>(sc.prims, tr)) { trav_terminate(tr); break; }
+        // ---- work loop.  Every pass the warp votes for one of two steps: a primitive step (each lane holding
+        // primitives tests ONE of them) when at least prim_min_lanes lanes hold some or nobody can descend, else a
+        // node step, in which lanes holding primitives push them for later and descend too if they can.
+        // (a lane without a ray keeps both groups empty, so "has work" is just "not done")
+        for (bool first = true;; first = false) {
+            const bool has_p = tr.Gt.y != 0;
+            const bool work = !trav_done(tr);
+            const unsigned wm = __ballot_sync(0xffffffffu, work);
+            if (wm == 0) break;
+            // refill once too few lanes are still traversing (never before the pass after a fetch made progress)
+            if (!first && !drained && __popc(wm) < a.refill_threshold) break;
+            const unsigned pm = __ballot_sync(0xffffffffu, has_p);
+            if (__popc(pm) >= a.prim_min_lanes || pm == wm) {
+                if (has_p) {
+                    prim_tests++;
+                    if (trav_prim<SHADOW>(sc.prims, tr)) trav_terminate(tr);
+                }
+            } else if (work) {
+                bool descend = !has_p;
+                if (has_p && tr.G.y != 0 && tr.sp < kTriPostponeMax) {
+                    tr.stack[tr.sp++] = tr.Gt;  // postpone these primitives, keep descending
+                    tr.Gt.y = 0;
+                    descend = true;
+                }
+                if (descend) {
+                    node_steps++;
+                    trav_node(sc.nodes8, tr);
                 }
             }
-            if (work && tr.Gt.y == 0) trav_next_group(tr);
-            // refill once too few lanes are still traversing (every pass makes progress before it may leave)
-            if (!drained && __popc(__ballot_sync(0xffffffffu, has_ray && !trav_done(tr))) < kRefillThreshold) break;
+            trav_next_group(tr);
         }
-        if (has_ray && trav_done(tr)) {
+        if (has_ray && trav_done(tr)) {  // finished (possibly in an earlier pass of this loop)
             if (SHADOW) {
                 if (tr.hit.prim == kNoHit) {
                     V4 r = a.pool.rad[slot], c = a.pool.sh_c[slot];
@@ -197,10 +210,13 @@ __global__ void __launch_bounds__(128) k_trace(const LJ_GRID_CONSTANT DevScene s
         }
     }
     warp_add(&a.counters[SHADOW ? C_SHADOW : C_CLOSEST], traced);
+    warp_add(&a.counters[C_NODE_STEPS], node_steps);
+    warp_add(&a.counters[C_PRIM_TESTS], prim_tests);
 }
 
 // K4
-__global__ void __launch_bounds__(128) k_shade(const LJ_GRID_CONSTANT DevScene sc, const LJ_GRID_CONSTANT WaveArgs a) {
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(128, MIN_BLOCKS) k_shade(const LJ_GRID_CONSTANT DevScene sc, const LJ_GRID_CONSTANT WaveArgs a) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     ShadeCounters cnt = {0, 0, 0, 0};
     if (i < a.pool.capacity) {
@@ -294,8 +310,9 @@ static int render_impl(lj_scene *s, const lj_render_opts *opts_in, float *d_out,
     if (d_var && !s->d_film_sq) LJ_CUDA(cudaMalloc(&s->d_film_sq, (size_t)npix * 16));
     unsigned long long *d_counters = nullptr;
     LJ_CUDA(cudaMalloc(&d_counters, sizeof(unsigned long long) * C_COUNT));
-    unsigned long long *h_counters = nullptr;
-    LJ_CUDA(cudaMallocHost(&h_counters, sizeof(unsigned long long) * C_COUNT));
+    unsigned long long *h_counters = nullptr;  // C_COUNT final counters, then the ring of per-wave live-path counts
+    LJ_CUDA(cudaMallocHost(&h_counters, sizeof(unsigned long long) * (C_COUNT + 8)));
+    unsigned long long *h_active = h_counters + C_COUNT;
 
     WaveArgs a;
     a.pool = s->pool;
@@ -311,6 +328,12 @@ static int render_impl(lj_scene *s, const lj_render_opts *opts_in, float *d_out,
     a.tiles_x = (w + 7) / 8;
     a.tiles_y = (h + 3) / 4;
     a.total_items = (unsigned long long)a.tiles_x * a.tiles_y * 32ull * (unsigned)(se - sb);
+    a.prim_min_lanes = kPrimMinLanes;
+    a.refill_threshold = kRefillThreshold;
+    if (const char *e = getenv("LJ_PRIM_MIN_LANES")) a.prim_min_lanes = atoi(e);
+    if (const char *e = getenv("LJ_REFILL")) a.refill_threshold = atoi(e);
+    int shade_occ = 4;  // resident CTAs per SM the shade kernel is compiled for (register cap), LJ_SHADE_OCC for tuning runs
+    if (const char *e = getenv("LJ_SHADE_OCC")) shade_occ = atoi(e);
 
     const int nb256 = (capacity + 255) / 256, nb128 = (capacity + 127) / 128;
     // persistent grid: exactly one wave of resident CTAs (SM count x the occupancy of k_trace)
@@ -340,27 +363,44 @@ static int render_impl(lj_scene *s, const lj_render_opts *opts_in, float *d_out,
     LJ_CUDA(cudaEventRecord(ev_begin, stream));
     LJ_LAUNCH(k_clear_pool, nb256, 256, stream, s->pool);
     launches++;
+    // The host runs kLookahead waves ahead of the device: the live-path count of wave w is copied to pinned memory
+    // right after its regen kernel and only read (after waiting for that copy) when wave w + kLookahead is being
+    // queued, so the stream never drains between waves.  The waves queued behind the first empty one find an
+    // empty pool and cost a few microseconds each.
+    constexpr int kLookahead = 2, kRing = 4;
+    cudaEvent_t ev_copied[kRing];
+    for (auto &e : ev_copied) e = evp.next();
+    uint64_t queued = 0;
     for (;;) {
         cudaEvent_t e0 = evp.next(), e1 = evp.next(), e2 = evp.next(), e3 = evp.next(), e4 = evp.next();
         LJ_CUDA(cudaMemsetAsync(&d_counters[C_ACTIVE], 0, sizeof(unsigned long long), stream));
         LJ_CUDA(cudaEventRecord(e0, stream));
         LJ_LAUNCH(k_regen, nb256, 256, stream, sc, a);
         LJ_CUDA(cudaEventRecord(e1, stream));
-        LJ_CUDA(cudaMemcpyAsync(h_counters, d_counters, sizeof(unsigned long long) * C_COUNT, cudaMemcpyDeviceToHost, stream));
+        LJ_CUDA(cudaMemcpyAsync(&h_active[queued % kRing], &d_counters[C_ACTIVE], sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+        LJ_CUDA(cudaEventRecord(ev_copied[queued % kRing], stream));
         launches++;
-        LJ_CUDA(cudaStreamSynchronize(stream));
-        if (h_counters[C_ACTIVE] == 0) { marks.push_back(e0); marks.push_back(e1); marks.push_back(nullptr); break; }
+        if (queued >= (uint64_t)kLookahead) {
+            uint64_t w = queued - kLookahead;
+            LJ_CUDA(cudaEventSynchronize(ev_copied[w % kRing]));
+            if (h_active[w % kRing] == 0) { waves = w; marks.push_back(e0); marks.push_back(e1); marks.push_back(nullptr); break; }
+        }
         LJ_CUDA(cudaMemsetAsync(d_cursors, 0, 2 * sizeof(unsigned int), stream));
         LJ_LAUNCH(k_trace<false>, trace_blocks, 128, stream, sc, a);
         LJ_CUDA(cudaEventRecord(e2, stream));
-        LJ_LAUNCH(k_shade, nb128, 128, stream, sc, a);
+        switch (shade_occ) {
+            case 5: LJ_LAUNCH(k_shade<5>, nb128, 128, stream, sc, a); break;
+            case 6: LJ_LAUNCH(k_shade<6>, nb128, 128, stream, sc, a); break;
+            case 8: LJ_LAUNCH(k_shade<8>, nb128, 128, stream, sc, a); break;
+            default: LJ_LAUNCH(k_shade<4>, nb128, 128, stream, sc, a); break;
+        }
         LJ_CUDA(cudaEventRecord(e3, stream));
         LJ_LAUNCH(k_trace<true>, trace_blocks, 128, stream, sc, a);
         LJ_CUDA(cudaEventRecord(e4, stream));
         launches += 3;
-        waves++;
+        queued++;
         marks.push_back(e0); marks.push_back(e1); marks.push_back(e2); marks.push_back(e3); marks.push_back(e4);
-        if (waves > 1000000) { set_error("wavefront loop did not terminate"); return LJ_ERR_CUDA; }
+        if (queued > 1000000) { set_error("wavefront loop did not terminate"); return LJ_ERR_CUDA; }
     }
     LJ_CUDA(cudaEventRecord(ev_end, stream));
     LJ_LAUNCH(k_resolve, (npix + 255) / 256, 256, stream, s->d_film, a.film_sq, npix, 1.f / (float)(se - sb), opts.normalize, d_out, d_var);
@@ -389,6 +429,8 @@ static int render_impl(lj_scene *s, const lj_render_opts *opts_in, float *d_out,
         stats->closest_rays = h_counters[C_CLOSEST];
         stats->shadow_rays = h_counters[C_SHADOW];
         stats->bounces = h_counters[C_BOUNCES];
+        stats->node_steps = h_counters[C_NODE_STEPS];
+        stats->prim_tests = h_counters[C_PRIM_TESTS];
         stats->kernel_launches = launches;
         stats->waves = waves;
         stats->extend_launches = stats->shade_launches = stats->shadow_launches = waves;
