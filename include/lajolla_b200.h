@@ -246,6 +246,15 @@ typedef struct lj_light_result {
 } lj_light_result;
 int lj_light_batch(lj_scene *scene, const lj_light_query *q, int64_t n, lj_light_result *out);
 
+/* Medium and phase-function queries (medium.h:25-31, phase_function.h:18-29) for medium `medium_id`:
+ *   majorant       = get_majorant(medium, Ray{org, dir, 0, tfar})          medium.cpp:27-29
+ *   sigma_a/_s     = get_sigma_a / get_sigma_s(medium, org + t * dir)      medium.cpp:31-37, volume.h:45-81
+ *   phase_dir      = sample_phase_function(phase, -dir, rnd)               phase_functions/ *.inl
+ *   phase_eval/pdf = eval / pdf_sample_phase(phase, -dir, phase_dir) */
+typedef struct lj_medium_query { float org[3], tfar, dir[3], t, rnd[2]; int32_t medium_id, _pad; } lj_medium_query;
+typedef struct lj_medium_result { float majorant[3], sigma_a[3], sigma_s[3], phase_dir[3], phase_eval, phase_pdf; } lj_medium_result;
+int lj_medium_batch(lj_scene *scene, const lj_medium_query *q, int64_t n, lj_medium_result *out);
+
 /* sample_primary (camera.cpp:23-47): screen_pos (x,y in [0,1]^2) -> ray. */
 int lj_camera_rays(lj_scene *scene, const float *screen_pos_xy, int64_t n, lj_ray *rays);
 

@@ -31,6 +31,10 @@ BSDF_RESULT_DTYPE = np.dtype([("f", "<f4", 3), ("pdf", "<f4"), ("sampled", "<i4"
 LIGHT_QUERY_DTYPE = np.dtype([("ref_point", "<f4", 3), ("rnd_uv", "<f4", 2), ("rnd_w", "<f4"), ("light_w", "<f4")])
 LIGHT_RESULT_DTYPE = np.dtype([("light_id", "<i4"), ("position", "<f4", 3), ("normal", "<f4", 3), ("pmf", "<f4"),
                                ("pdf", "<f4"), ("emission", "<f4", 3)])
+MEDIUM_QUERY_DTYPE = np.dtype([("org", "<f4", 3), ("tfar", "<f4"), ("dir", "<f4", 3), ("t", "<f4"), ("rnd", "<f4", 2),
+                               ("medium_id", "<i4"), ("_pad", "<i4")])
+MEDIUM_RESULT_DTYPE = np.dtype([("majorant", "<f4", 3), ("sigma_a", "<f4", 3), ("sigma_s", "<f4", 3), ("phase_dir", "<f4", 3),
+                                ("phase_eval", "<f4"), ("phase_pdf", "<f4")])
 
 assert RAY_DTYPE.itemsize == C.sizeof(abi.lj_ray) and HIT_DTYPE.itemsize == C.sizeof(abi.lj_hit)
 assert VERTEX_DTYPE.itemsize == C.sizeof(abi.lj_vertex)
@@ -38,6 +42,8 @@ assert BSDF_QUERY_DTYPE.itemsize == C.sizeof(abi.lj_bsdf_query)
 assert BSDF_RESULT_DTYPE.itemsize == C.sizeof(abi.lj_bsdf_result)
 assert LIGHT_QUERY_DTYPE.itemsize == C.sizeof(abi.lj_light_query)
 assert LIGHT_RESULT_DTYPE.itemsize == C.sizeof(abi.lj_light_result)
+assert MEDIUM_QUERY_DTYPE.itemsize == C.sizeof(abi.lj_medium_query)
+assert MEDIUM_RESULT_DTYPE.itemsize == C.sizeof(abi.lj_medium_result)
 
 
 def _ptr(a, ctype):
@@ -137,6 +143,13 @@ class Scene:
         q = np.ascontiguousarray(queries, dtype=LIGHT_QUERY_DTYPE)
         out = np.zeros(q.shape[0], dtype=LIGHT_RESULT_DTYPE)
         abi.check(self._lib.lj_light_batch(self._h, _ptr(q, abi.lj_light_query), q.shape[0], _ptr(out, abi.lj_light_result)))
+        return out
+
+    def medium(self, queries):
+        """get_majorant / get_sigma_a / get_sigma_s (medium.h:25-27) and the phase function (phase_function.h:18-29)."""
+        q = np.ascontiguousarray(queries, dtype=MEDIUM_QUERY_DTYPE)
+        out = np.zeros(q.shape[0], dtype=MEDIUM_RESULT_DTYPE)
+        abi.check(self._lib.lj_medium_batch(self._h, _ptr(q, abi.lj_medium_query), q.shape[0], _ptr(out, abi.lj_medium_result)))
         return out
 
     def sample_primary(self, screen_pos):

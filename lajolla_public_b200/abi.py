@@ -112,6 +112,15 @@ class lj_light_query(C.Structure):
     _fields_ = [("ref_point", f32 * 3), ("rnd_uv", f32 * 2), ("rnd_w", f32), ("light_w", f32)]
 
 
+class lj_medium_query(C.Structure):
+    _fields_ = [("org", f32 * 3), ("tfar", f32), ("dir", f32 * 3), ("t", f32), ("rnd", f32 * 2), ("medium_id", i32), ("_pad", i32)]
+
+
+class lj_medium_result(C.Structure):
+    _fields_ = [("majorant", f32 * 3), ("sigma_a", f32 * 3), ("sigma_s", f32 * 3), ("phase_dir", f32 * 3),
+                ("phase_eval", f32), ("phase_pdf", f32)]
+
+
 class lj_light_result(C.Structure):
     _fields_ = [("light_id", i32), ("position", f32 * 3), ("normal", f32 * 3), ("pmf", f32), ("pdf", f32),
                 ("emission", f32 * 3)]
@@ -137,6 +146,7 @@ PROTOTYPES = {
     "lj_intersect": (C.c_int, [C.c_void_p, C.POINTER(lj_ray), pf32, i64, C.POINTER(lj_vertex)]),
     "lj_bsdf_batch": (C.c_int, [C.c_void_p, C.POINTER(lj_bsdf_query), i64, C.POINTER(lj_bsdf_result)]),
     "lj_light_batch": (C.c_int, [C.c_void_p, C.POINTER(lj_light_query), i64, C.POINTER(lj_light_result)]),
+    "lj_medium_batch": (C.c_int, [C.c_void_p, C.POINTER(lj_medium_query), i64, C.POINTER(lj_medium_result)]),
     "lj_camera_rays": (C.c_int, [C.c_void_p, pf32, i64, C.POINTER(lj_ray)]),
     "lj_texture_batch": (C.c_int, [C.c_void_p, i32, i32, pf32, i64, pf32]),
     "lj_pcg32_batch": (C.c_int, [u64, u64, i32, i32, C.POINTER(u32), pf32]),

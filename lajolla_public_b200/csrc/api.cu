@@ -3,6 +3,7 @@
 // the reference's own object code).  Every entry point runs the same LJ_HD device functions the
 // wavefront kernels call.
 #include "scene.cuh"
+#include "lj_media.h"
 
 namespace lj {
 namespace {
@@ -109,6 +110,24 @@ __global__ void __launch_bounds__(128) k_bsdf(const LJ_GRID_CONSTANT DevScene sc
             r.s_roughness = s.roughness;
         }
     }
+    out[i] = r;
+}
+
+__global__ void __launch_bounds__(128) k_medium(const LJ_GRID_CONSTANT DevScene sc, const lj_medium_query *q, long long n, lj_medium_result *out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    lj_medium_query in = q[i];
+    const DevMedium &m = sc.media[in.medium_id];
+    V3 o = v3_in(in.org), d = v3_in(in.dir);
+    lj_medium_result r;
+    v3_out(r.majorant, medium_majorant(m, o, d, in.tfar));
+    V3 sa, ss;
+    medium_sigmas(m, o + d * in.t, sa, ss);
+    v3_out(r.sigma_a, sa); v3_out(r.sigma_s, ss);
+    V3 pd = phase_sample(m, -d, mk2(in.rnd[0], in.rnd[1]));
+    v3_out(r.phase_dir, pd);
+    r.phase_eval = phase_eval(m, -d, pd);
+    r.phase_pdf = phase_pdf(m, -d, pd);
     out[i] = r;
 }
 
@@ -230,6 +249,21 @@ extern "C" int lj_bsdf_batch(lj_scene *s, const lj_bsdf_query *q, int64_t n, lj_
     LJ_CUDA(dq.err); LJ_CUDA(dr.err);
     LJ_CUDA(dq.up(q, n));
     LJ_LAUNCH(k_bsdf, grid_for(n, 128), 128, s->stream, s->dev, dq.p, n, dr.p);
+    LJ_CUDA(cudaStreamSynchronize(s->stream));
+    LJ_CUDA(cudaGetLastError());
+    LJ_CUDA(dr.down(out, n));
+    return LJ_OK;
+}
+
+extern "C" int lj_medium_batch(lj_scene *s, const lj_medium_query *q, int64_t n, lj_medium_result *out) {
+    LJ_CHECK_ARGS(s && q && out && n >= 0);
+    if (n == 0) return LJ_OK;
+    for (int64_t i = 0; i < n; i++)
+        if (q[i].medium_id < 0 || q[i].medium_id >= s->dev.num_media) { set_error("medium id out of range"); return LJ_ERR_INVALID; }
+    DevBuf<lj_medium_query> dq(n); DevBuf<lj_medium_result> dr(n);
+    LJ_CUDA(dq.err); LJ_CUDA(dr.err);
+    LJ_CUDA(dq.up(q, n));
+    LJ_LAUNCH(k_medium, grid_for(n, 128), 128, s->stream, s->dev, dq.p, n, dr.p);
     LJ_CUDA(cudaStreamSynchronize(s->stream));
     LJ_CUDA(cudaGetLastError());
     LJ_CUDA(dr.down(out, n));

@@ -93,7 +93,9 @@ LJ_HD void coordinate_system(V3 n, V3 &a, V3 &b) {
         a = mk3(0, -1, 0);
         b = mk3(-1, 0, 0);
     } else {
-        float s = 1 / (1 + n.z);
+        // Same frame as frame.h:6-17.  In fp32 1 + n.z cancels near the pole (the reference is double), so
+        // below the equator 1 / (1 + n.z) is taken from the unit-length identity (1 - n.z) / (n.x^2 + n.y^2).
+        float s = n.z < -0.5f ? (1 - n.z) / (n.x * n.x + n.y * n.y) : 1 / (1 + n.z);
         float t = -n.x * n.y * s;
         a = mk3(1 - n.x * n.x * s, t, -n.x);
         b = mk3(t, 1 - n.y * n.y * s, -n.y);

@@ -1,0 +1,186 @@
+// lj_media.h -- participating media and phase functions in device memory.
+// fp32 restatement of the reference's medium.cpp:27-37, media/homogeneous.inl:1-11,
+// media/heterogeneous.inl:3-21, volume.h:45-81 (trilinear GridVolume lookup), :125-144 (slab test),
+// phase_functions/isotropic.inl:1-15, phase_functions/henyeygreenstein.inl:3-48, and of the two
+// tracking loops of the course handout the public reference leaves as homework
+// (handouts/homework2.tex:713-758 chromatic delta tracking, :771-810 ratio tracking; our CPU
+// restatement of the same text is oracle/overlay/hw_vol_path_tracing.h).
+#pragma once
+#include "lj_pcg.h"
+#include "lj_scene_dev.h"
+
+namespace lj {
+
+// volume.h:45-81.  Zero outside the grid box, (res - 1) scaling, int() truncation, scale applied last.
+LJ_HD V3 volume_lookup(const DevVolume &v, V3 p) {
+    if (!v.is_grid) return mk3(v.value[0], v.value[1], v.value[2]);
+    float px = (p.x - v.p_min[0]) / (v.p_max[0] - v.p_min[0]);
+    float py = (p.y - v.p_min[1]) / (v.p_max[1] - v.p_min[1]);
+    float pz = (p.z - v.p_min[2]) / (v.p_max[2] - v.p_min[2]);
+    if (px < 0 || px > 1 || py < 0 || py > 1 || pz < 0 || pz > 1) return mk3(0);
+    const int nx = v.res[0], ny = v.res[1], nz = v.res[2];
+    px *= (float)(nx - 1); py *= (float)(ny - 1); pz *= (float)(nz - 1);
+    int x0 = clampi((int)px, 0, nx - 1), y0 = clampi((int)py, 0, ny - 1), z0 = clampi((int)pz, 0, nz - 1);
+    int x1 = clampi(x0 + 1, 0, nx - 1), y1 = clampi(y0 + 1, 0, ny - 1), z1 = clampi(z0 + 1, 0, nz - 1);
+    float dx = px - x0, dy = py - y0, dz = pz - z0;
+    const V4 *d = v.data;
+    V3 v000 = xyz(ld4(&d[(z0 * ny + y0) * nx + x0])), v001 = xyz(ld4(&d[(z0 * ny + y0) * nx + x1]));
+    V3 v010 = xyz(ld4(&d[(z0 * ny + y1) * nx + x0])), v011 = xyz(ld4(&d[(z0 * ny + y1) * nx + x1]));
+    V3 v100 = xyz(ld4(&d[(z1 * ny + y0) * nx + x0])), v101 = xyz(ld4(&d[(z1 * ny + y0) * nx + x1]));
+    V3 v110 = xyz(ld4(&d[(z1 * ny + y1) * nx + x0])), v111 = xyz(ld4(&d[(z1 * ny + y1) * nx + x1]));
+    V3 r = v000 * ((1 - dx) * (1 - dy) * (1 - dz)) + v001 * (dx * (1 - dy) * (1 - dz)) +
+           v010 * ((1 - dx) * dy * (1 - dz)) + v011 * (dx * dy * (1 - dz)) +
+           v100 * ((1 - dx) * (1 - dy) * dz) + v101 * (dx * (1 - dy) * dz) +
+           v110 * ((1 - dx) * dy * dz) + v111 * (dx * dy * dz);
+    return r * v.scale;
+}
+
+// volume.h:125-144: does [0, tfar] of the ray overlap the grid box (a constant volume is everywhere)
+LJ_HD bool volume_intersect(const DevVolume &v, V3 o, V3 d, float tfar) {
+    if (!v.is_grid) return true;
+    float t0 = 0, t1 = tfar;
+    const float oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z};
+    for (int i = 0; i < 3; i++) {
+        float tn = (v.p_min[i] - oo[i]) / dd[i];
+        float tf = (v.p_max[i] - oo[i]) / dd[i];
+        if (tn > tf) { float s = tn; tn = tf; tf = s; }
+        t0 = tn > t0 ? tn : t0;
+        t1 = tf < t1 ? tf : t1;
+        if (t0 > t1) return false;
+    }
+    return true;
+}
+
+LJ_HD V3 volume_max(const DevVolume &v) {  // volume.h get_max_value
+    if (!v.is_grid) return mk3(v.value[0], v.value[1], v.value[2]);
+    return mk3(v.max_data[0], v.max_data[1], v.max_data[2]) * v.scale;
+}
+
+// medium.cpp:27-37
+LJ_HD V3 medium_majorant(const DevMedium &m, V3 o, V3 d, float tfar) {
+    if (m.type == 0) return mk3(m.sigma_a[0] + m.sigma_s[0], m.sigma_a[1] + m.sigma_s[1], m.sigma_a[2] + m.sigma_s[2]);
+    return volume_intersect(m.density, o, d, tfar) ? volume_max(m.density) : mk3(0);
+}
+LJ_HD void medium_sigmas(const DevMedium &m, V3 p, V3 &sigma_a, V3 &sigma_s) {
+    if (m.type == 0) {
+        sigma_a = mk3(m.sigma_a[0], m.sigma_a[1], m.sigma_a[2]);
+        sigma_s = mk3(m.sigma_s[0], m.sigma_s[1], m.sigma_s[2]);
+        return;
+    }
+    V3 density = volume_lookup(m.density, p), albedo = volume_lookup(m.albedo, p);
+    sigma_s = density * albedo;
+    sigma_a = density * (mk3(1) - albedo);
+}
+
+// ---- phase functions.  dir_in points away from the scattering point (hence +2g cos, henyeygreenstein.inl:3-7)
+LJ_HD float phase_eval(const DevMedium &m, V3 dir_in, V3 dir_out) {
+    if (m.phase_type == 0) return kInvFourPi;
+    float g = m.phase_g;
+    float base = 1 + g * g + 2 * g * dot(dir_in, dir_out);
+    return kInvFourPi * (1 - g * g) / (base * sqrtf(base));
+}
+LJ_HD float phase_pdf(const DevMedium &m, V3 dir_in, V3 dir_out) { return phase_eval(m, dir_in, dir_out); }
+LJ_HD V3 phase_sample(const DevMedium &m, V3 dir_in, V2 u) {
+    float g = m.phase_g;
+    if (m.phase_type == 0 || fabsf(g) < 1e-3f) {
+        float z = 1 - 2 * u.x;
+        float r = sqrtf(fmaxf(0.f, 1 - z * z));
+        float phi = 2 * kPi * u.y;
+        return mk3(r * cosf(phi), r * sinf(phi), z);
+    }
+    float tmp = (g * g - 1) / (2 * u.x * g - (g + 1));
+    float cos_el = (tmp * tmp - (1 + g * g)) / (2 * g);
+    float sin_el = sqrtf(fmaxf(1 - cos_el * cos_el, 0.f));
+    float az = 2 * kPi * u.y;
+    Frame f = make_frame(dir_in);
+    return to_world(f, mk3(sin_el * cosf(az), sin_el * sinf(az), cos_el));
+}
+
+// Both tracking loops multiply three running products (transmittance and the two pdfs) by exp(-majorant * t) at
+// every step.  Only ratios of those products are ever consumed -- transmittance / avg(pdf), and the two pdfs
+// against each other inside the MIS weight -- so the factor exp(-min(majorant) * t) common to all channels of all
+// three cancels exactly.  It is dropped here: in fp32 exp(-100 * 1.4) underflows where the reference's double does
+// not (hetvol: majorant 100 over an empty stretch of the grid), which would silently zero long segments.
+LJ_HD V3 tracking_exp(V3 majorant_minus_min, float t) {
+    return mk3(majorant_minus_min.x > 0 ? expf(-majorant_minus_min.x * t) : 1.f,
+               majorant_minus_min.y > 0 ? expf(-majorant_minus_min.y * t) : 1.f,
+               majorant_minus_min.z > 0 ? expf(-majorant_minus_min.z * t) : 1.f);
+}
+
+LJ_HD int tracking_channel(float u) { return clampi((int)(u * 3), 0, 2); }
+
+// homework2.tex:713-758.  Free flight over [0, t_hit] of the ray (o, d) by chromatic delta tracking.
+// Returns true on a real collision at distance accum_t; the three running products are updated in place.
+LJ_HD bool free_flight(const DevMedium &m, V3 o, V3 d, float ray_tfar, float t_hit, int max_null, Pcg &rng,
+                       V3 &transmittance, V3 &trans_dir_pdf, V3 &trans_nee_pdf, float &accum_t) {
+    V3 majorant = medium_majorant(m, o, d, ray_tfar);
+    int channel = tracking_channel(pcg_uniform(rng));
+    float max_maj = max3(majorant);
+    float maj_c = comp(majorant, channel);
+    accum_t = 0;
+    if (!(maj_c > 0)) return false;
+    const V3 maj_rel = majorant - mk3(min3(majorant));  // see tracking_exp
+    for (int it = 0; it < max_null; it++) {
+        float t = -logf(1 - pcg_uniform(rng)) / maj_c;
+        float dt = t_hit - accum_t;
+        accum_t = fminf(accum_t + t, t_hit);
+        if (t < dt) {
+            V3 sa, ss;
+            medium_sigmas(m, o + d * accum_t, sa, ss);
+            V3 sigma_t = sa + ss;
+            V3 real_prob = sigma_t / majorant;
+            V3 e = tracking_exp(maj_rel, t);
+            if (pcg_uniform(rng) < comp(real_prob, channel)) {
+                transmittance *= e / max_maj;
+                trans_dir_pdf *= e * majorant * real_prob / max_maj;
+                return true;
+            }
+            transmittance *= e * (majorant - sigma_t) / max_maj;
+            trans_dir_pdf *= e * majorant * (mk3(1) - real_prob) / max_maj;
+            trans_nee_pdf *= e * majorant / max_maj;
+        } else {
+            V3 e = tracking_exp(maj_rel, dt);
+            transmittance *= e;
+            trans_dir_pdf *= e;
+            trans_nee_pdf *= e;
+            return false;
+        }
+    }
+    return false;
+}
+
+// homework2.tex:771-810.  Ratio tracking over one segment [0, next_t] of the shadow ray (o, d).
+LJ_HD void ratio_track(const DevMedium &m, V3 o, V3 d, float ray_tfar, float next_t, int max_null, Pcg &rng,
+                       V3 &T_light, V3 &p_trans_nee, V3 &p_trans_dir) {
+    V3 majorant = medium_majorant(m, o, d, ray_tfar);
+    int channel = tracking_channel(pcg_uniform(rng));
+    float max_maj = max3(majorant);
+    float maj_c = comp(majorant, channel);
+    if (!(maj_c > 0)) return;
+    const V3 maj_rel = majorant - mk3(min3(majorant));
+    float accum_t = 0;
+    for (int it = 0; it < max_null; it++) {
+        float t = -logf(1 - pcg_uniform(rng)) / maj_c;
+        float dt = next_t - accum_t;
+        accum_t = fminf(accum_t + t, next_t);
+        if (t < dt) {
+            V3 sa, ss;
+            medium_sigmas(m, o + d * accum_t, sa, ss);
+            V3 sigma_t = sa + ss;
+            V3 real_prob = sigma_t / majorant;
+            V3 e = tracking_exp(maj_rel, t);
+            T_light *= e * (majorant - sigma_t) / max_maj;
+            p_trans_nee *= e * majorant / max_maj;
+            p_trans_dir *= e * majorant * (mk3(1) - real_prob) / max_maj;
+            if (max3(T_light) <= 0) return;
+        } else {
+            V3 e = tracking_exp(maj_rel, dt);
+            T_light *= e;
+            p_trans_nee *= e;
+            p_trans_dir *= e;
+            return;
+        }
+    }
+}
+
+}  // namespace lj

@@ -26,6 +26,13 @@ struct PathPool {
     V4 *sh_c;   // NEE contribution if unoccluded .xyz, -
     V4 *meta;   // bits(pixel), bits(nv | flags<<16), bits(rng lo), bits(rng hi)
     V4 *aux;    // eta_scale, ray spread, bits(sample index), bits(medium id)
+    // volpath only (null for the path integrator): MIS caches of homework2.tex:521-558 and the NEE walk record
+    V4 *vol0;   // multi_trans_dir_pdf.xyz, -
+    V4 *vol1;   // multi_trans_nee_pdf.xyz, -
+    V4 *vol2;   // nee_p_cache.xyz, -
+    V4 *sh_o;   // walk origin.xyz, bits((medium + 1) & 0xffff | budget << 16)
+    V4 *sh_pl;  // light point.xyz, bits(walk rng seed)
+                // (volpath reuses sh_d.w as pdf_dir = pdf_scatter * G, < 0: no walk; sh_c.w as pdf_nee)
     int capacity;
 };
 
@@ -44,6 +51,12 @@ struct PathState {
     uint64_t rng_state;
     float eta_scale, spread;
     int medium;
+    // volpath (lj_volpath.h); nv counts `bounces` there
+    V3 mt_dir, mt_nee, nee_p;
+    V3 sh_o, sh_pl;
+    float sh_pdf_nee, sh_pdf_dir;
+    int sh_medium;
+    uint32_t sh_budget, sh_seed;
 };
 
 struct RenderParams {
@@ -87,6 +100,8 @@ LJ_HD void generate_path(const DevScene &sc, const RenderParams &rp, uint32_t pi
     s.medium = sc.camera.medium_id;
     s.hit.prim = kNoHit;
     s.hit.t = 0; s.hit.u = 0; s.hit.v = 0;
+    s.mt_dir = mk3(1); s.mt_nee = mk3(1); s.nee_p = mk3(0);
+    s.sh_pdf_dir = -1;
 }
 
 LJ_HD float mis_power(float pa, float pb) { return (pa * pa) / (pa * pa + pb * pb); }
@@ -245,6 +260,30 @@ LJ_HD void store_state(const PathPool &p, int i, const PathState &s, bool store_
     if (s.sh_tfar >= 0) p.sh_c[i] = mk4(s.sh_c, 0.f);
     p.meta[i] = mk4(u2f(s.pixel), u2f((s.nv & 0xffffu) | s.flags), u2f((uint32_t)s.rng_state), u2f((uint32_t)(s.rng_state >> 32)));
     p.aux[i] = mk4(s.eta_scale, s.spread, u2f(s.sample), u2f((uint32_t)s.medium));
+}
+
+// volpath: the common fields plus the MIS caches and the NEE walk record
+LJ_HD void load_state_vol(const PathPool &p, int i, PathState &s) {
+    load_state(p, i, s);
+    s.mt_dir = xyz(p.vol0[i]); s.mt_nee = xyz(p.vol1[i]); s.nee_p = xyz(p.vol2[i]);
+    s.sh_pdf_dir = -1;
+}
+LJ_HD void store_state_vol(const PathPool &p, int i, const PathState &s, bool store_ray) {
+    if (store_ray) {
+        p.ray_o[i] = mk4(s.o, s.tnear);
+        p.ray_d[i] = mk4(s.d, s.tfar);
+    }
+    p.thr[i] = mk4(s.T, s.pdf_sa);
+    p.rad[i] = mk4(s.L, s.rr_prob);
+    p.meta[i] = mk4(u2f(s.pixel), u2f((s.nv & 0xffffu) | s.flags), u2f((uint32_t)s.rng_state), u2f((uint32_t)(s.rng_state >> 32)));
+    p.aux[i] = mk4(s.eta_scale, s.spread, u2f(s.sample), u2f((uint32_t)s.medium));
+    p.vol0[i] = mk4(s.mt_dir, 0.f); p.vol1[i] = mk4(s.mt_nee, 0.f); p.vol2[i] = mk4(s.nee_p, 0.f);
+    p.sh_d[i] = mk4(s.sh_d, s.sh_pdf_dir);
+    if (s.sh_pdf_dir >= 0) {
+        p.sh_c[i] = mk4(s.sh_c, s.sh_pdf_nee);
+        p.sh_o[i] = mk4(s.sh_o, u2f((uint32_t)((s.sh_medium + 1) & 0xffff) | (s.sh_budget << 16)));
+        p.sh_pl[i] = mk4(s.sh_pl, u2f(s.sh_seed));
+    }
 }
 
 }  // namespace lj

@@ -11,7 +11,9 @@
 // measured: index queues made k_shade 2x slower through uncoalesced record access
 // (profiles/r01_b_*).
 #include "scene.cuh"
+#include "lj_volpath.h"
 
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <algorithm>
@@ -91,7 +93,7 @@ __global__ void __launch_bounds__(256) k_regen(const LJ_GRID_CONSTANT DevScene s
         if (ok) {
             PathState s;
             generate_path(sc, a.rp, y * a.rp.width + x, sample, s);
-            store_state(a.pool, i, s, true);
+            if (a.pool.vol0) store_state_vol(a.pool, i, s, true); else store_state(a.pool, i, s, true);
             a.pool.hit[i] = mk4(0, 0, 0, u2f((uint32_t)kNoHit));
             started = 1;
         } else if (flags) {
@@ -115,10 +117,17 @@ __global__ void __launch_bounds__(256) k_regen(const LJ_GRID_CONSTANT DevScene s
 constexpr int kRefillThreshold = 20;  // defaults; LJ_REFILL / LJ_PRIM_MIN_LANES override them for tuning runs
 constexpr int kPrimMinLanes = 12;
 
-template <bool SHADOW>
+// MODE 2 (volpath NEE walk, homework2.tex:459-510): the lane keeps its slot across the segments of one walk --
+// each segment is a closest-hit traversal, followed by ratio tracking over it and the index-matched / opaque test
+// (nee_walk_step); the walk's transmittance products stay in registers until the segment chain ends.
+template <int MODE>
 __global__ void __launch_bounds__(128) k_trace(const LJ_GRID_CONSTANT DevScene sc, const LJ_GRID_CONSTANT WaveArgs a) {
+    constexpr bool SHADOW = MODE == 1;
+    constexpr bool WALK = MODE == 2;
+    NeeWalk wk;
+    float seg_tfar = 0;
     const unsigned n = (unsigned)a.pool.capacity;
-    unsigned int *cursor = &a.cursors[SHADOW ? 1 : 0];
+    unsigned int *cursor = &a.cursors[MODE == 0 ? 0 : 1];
     const int lane = LJ_LANE();
     Trav tr;
     trav_terminate(tr);
@@ -139,7 +148,25 @@ __global__ void __launch_bounds__(128) k_trace(const LJ_GRID_CONSTANT DevScene s
                 unsigned idx = base + __popc(want & ((1u << lane) - 1));
                 if (idx < n) {
                     slot = (int)idx;
-                    if (SHADOW) {
+                    if (WALK) {
+                        V4 sd = a.pool.sh_d[slot];
+                        if (sd.w >= 0) {
+                            V4 so = a.pool.sh_o[slot], pl = a.pool.sh_pl[slot], cc = a.pool.sh_c[slot];
+                            uint32_t mb = f2u(so.w);
+                            wk.pc = xyz(so); wk.dir = xyz(sd); wk.pl = xyz(pl);
+                            wk.T_light = mk3(1); wk.p_nee = mk3(1); wk.p_dir = mk3(1);
+                            wk.c = xyz(cc); wk.pdf_nee = cc.w; wk.pdf_dir = sd.w;
+                            wk.medium = (int)(mb & 0xffffu) - 1;
+                            wk.budget = mb >> 16;
+                            wk.shadow_bounces = 0;
+                            wk.rng = pcg_init(((uint64_t)(unsigned)slot << 32) | f2u(pl.w), a.rp.seed);
+                            float tn;
+                            nee_walk_segment(sc, wk, tn, seg_tfar);
+                            trav_init(tr, wk.pc, wk.dir, tn, seg_tfar);
+                            a.pool.sh_d[slot] = mk4(sd.x, sd.y, sd.z, -1.f);
+                            has_ray = true;
+                        }
+                    } else if (SHADOW) {
                         V4 sd = a.pool.sh_d[slot];
                         if (sd.w >= 0) {
                             // The segment starts at the shaded vertex: pool.ray_o if the path continued (the
@@ -180,7 +207,7 @@ __global__ void __launch_bounds__(128) k_trace(const LJ_GRID_CONSTANT DevScene s
             if (__popc(pm) >= a.prim_min_lanes || pm == wm) {
                 if (has_p) {
                     prim_tests++;
-                    if (trav_prim<SHADOW>(sc.prims, tr)) trav_terminate(tr);
+                    if (trav_prim<SHADOW>(sc.prims, tr)) trav_terminate(tr);  // any-hit ends at the first hit
                 }
             } else if (work) {
                 bool descend = !has_p;
@@ -197,7 +224,22 @@ __global__ void __launch_bounds__(128) k_trace(const LJ_GRID_CONSTANT DevScene s
             trav_next_group(tr);
         }
         if (has_ray && trav_done(tr)) {  // finished (possibly in an earlier pass of this loop)
-            if (SHADOW) {
+            if (WALK) {
+                trav_finish_closest(sc.prims, tr);
+                V3 contrib;
+                if (nee_walk_step(sc, wk, tr.hit, seg_tfar, contrib)) {
+                    if (max3(contrib) > 0 || min3(contrib) < 0 || contrib.x != contrib.x || contrib.y != contrib.y || contrib.z != contrib.z) {
+                        V4 r = a.pool.rad[slot];
+                        a.pool.rad[slot] = mk4(r.x + contrib.x, r.y + contrib.y, r.z + contrib.z, r.w);
+                    }
+                    has_ray = false;
+                } else {  // next segment of the same walk
+                    float tn;
+                    nee_walk_segment(sc, wk, tn, seg_tfar);
+                    trav_init(tr, wk.pc, wk.dir, tn, seg_tfar);
+                    traced++;
+                }
+            } else if (SHADOW) {
                 if (tr.hit.prim == kNoHit) {
                     V4 r = a.pool.rad[slot], c = a.pool.sh_c[slot];
                     a.pool.rad[slot] = mk4(r.x + c.x, r.y + c.y, r.z + c.z, r.w);
@@ -206,10 +248,10 @@ __global__ void __launch_bounds__(128) k_trace(const LJ_GRID_CONSTANT DevScene s
                 trav_finish_closest(sc.prims, tr);
                 a.pool.hit[slot] = mk4(tr.hit.t, tr.hit.u, tr.hit.v, u2f((uint32_t)tr.hit.prim));
             }
-            has_ray = false;
+            if (!WALK) has_ray = false;
         }
     }
-    warp_add(&a.counters[SHADOW ? C_SHADOW : C_CLOSEST], traced);
+    warp_add(&a.counters[MODE == 0 ? C_CLOSEST : C_SHADOW], traced);
     warp_add(&a.counters[C_NODE_STEPS], node_steps);
     warp_add(&a.counters[C_PRIM_TESTS], prim_tests);
 }
@@ -224,8 +266,36 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_shade(const LJ_GRID_CONSTAN
         if (flags & kAlive) {
             PathState s;
             load_state(a.pool, i, s);
+#if defined(LJ_HOSTSIM)  // test-build tracing of one pixel's paths (LJ_DBG_PIXEL=y*w+x)
+            static const char *dbg = getenv("LJ_DBG_PIXEL");
+            const bool trace = dbg && (uint32_t)atoi(dbg) == s.pixel;
+            V3 T0 = s.T, L0 = s.L, o0 = s.o, d0 = s.d;
+#endif
             shade_path(sc, a.rp, s, cnt);
+#if defined(LJ_HOSTSIM)
+            if (trace) fprintf(stderr, "RAY %.9g %.9g %.9g %.9g %.9g %.9g OUT %.9g %.9g %.9g\n", o0.x, o0.y, o0.z, d0.x, d0.y, d0.z, s.d.x, s.d.y, s.d.z);
+            if (trace)
+                fprintf(stderr, "px %u smp %u nv %u prim %d t %g | T %g %g %g -> %g %g %g pdf %g | L %g -> %g | sh %g c %g %g %g | alive %d\n", s.pixel, s.sample,
+                        s.nv, s.hit.prim, s.hit.t, T0.x, T0.y, T0.z, s.T.x, s.T.y, s.T.z, s.pdf_sa, L0.x, s.L.x, s.sh_tfar, s.sh_c.x, s.sh_c.y, s.sh_c.z,
+                        (s.flags & kAlive) != 0);
+#endif
             store_state(a.pool, i, s, (s.flags & kAlive) != 0);
+        }
+    }
+    warp_add(&a.counters[C_BOUNCES], cnt.bounces);
+}
+
+// K4 + K5 for the volpath integrator (lj_volpath.h)
+__global__ void __launch_bounds__(128) k_shade_vol(const LJ_GRID_CONSTANT DevScene sc, const LJ_GRID_CONSTANT WaveArgs a) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    ShadeCounters cnt = {0, 0, 0, 0};
+    if (i < a.pool.capacity) {
+        uint32_t flags = f2u(a.pool.meta[i].y);
+        if (flags & kAlive) {
+            PathState s;
+            load_state_vol(a.pool, i, s);
+            shade_vol_path(sc, a.rp, s, cnt);
+            store_state_vol(a.pool, i, s, (s.flags & kAlive) != 0);
         }
     }
     warp_add(&a.counters[C_BOUNCES], cnt.bounces);
@@ -259,16 +329,21 @@ __global__ void k_resolve(const float *film, const float *film_sq, int npix, flo
     }
 }
 
-static int ensure_pool(lj_scene *s, int capacity) {
-    if (s->pool_capacity == capacity && s->pool_block) return LJ_OK;
+static int ensure_pool(lj_scene *s, int capacity, bool vol) {
+    if (s->pool_capacity == capacity && s->pool_block && (s->pool.vol0 != nullptr) == vol) return LJ_OK;
     if (s->pool_block) { cudaFree(s->pool_block); s->pool_block = nullptr; }
-    const int kFields = 9;
+    const int kFields = vol ? 14 : 9;
     LJ_CUDA(cudaMalloc(&s->pool_block, (size_t)capacity * sizeof(V4) * kFields));
     V4 *base = (V4 *)s->pool_block;
     PathPool &p = s->pool;
     p.ray_o = base + (size_t)capacity * 0; p.ray_d = base + (size_t)capacity * 1; p.hit = base + (size_t)capacity * 2;
     p.thr = base + (size_t)capacity * 3; p.rad = base + (size_t)capacity * 4; p.sh_d = base + (size_t)capacity * 5;
     p.sh_c = base + (size_t)capacity * 6; p.meta = base + (size_t)capacity * 7; p.aux = base + (size_t)capacity * 8;
+    p.vol0 = p.vol1 = p.vol2 = p.sh_o = p.sh_pl = nullptr;
+    if (vol) {
+        p.vol0 = base + (size_t)capacity * 9; p.vol1 = base + (size_t)capacity * 10; p.vol2 = base + (size_t)capacity * 11;
+        p.sh_o = base + (size_t)capacity * 12; p.sh_pl = base + (size_t)capacity * 13;
+    }
     p.capacity = capacity;
     s->pool_capacity = capacity;
     return LJ_OK;
@@ -289,8 +364,13 @@ static int render_impl(lj_scene *s, const lj_render_opts *opts_in, float *d_out,
     memset(&opts, 0, sizeof(opts));
     if (opts_in) opts = *opts_in;
     const DevScene &sc = s->dev;
-    if (sc.options.integrator != LJ_INT_PATH) {
-        set_error("integrator not supported by this build of the device path");
+    if (sc.options.integrator != LJ_INT_PATH && sc.options.integrator != LJ_INT_VOLPATH) {
+        set_error("integrator not supported by the device path (path and volpath are)");
+        return LJ_ERR_UNSUPPORTED;
+    }
+    const bool vol = sc.options.integrator == LJ_INT_VOLPATH;
+    if (vol && sc.envmap_light_id >= 0) {  // homework2.tex:196
+        set_error("volpath does not support environment maps");
         return LJ_ERR_UNSUPPORTED;
     }
     int spp = opts.spp > 0 ? opts.spp : sc.options.spp;
@@ -304,7 +384,7 @@ static int render_impl(lj_scene *s, const lj_render_opts *opts_in, float *d_out,
         unsigned long long want = (unsigned long long)npix * (unsigned)(se - sb);
         if (want < (unsigned long long)capacity) capacity = (int)((want + 255) / 256 * 256);
     }
-    int r = ensure_pool(s, capacity);
+    int r = ensure_pool(s, capacity, vol);
     if (r != LJ_OK) return r;
     if (!s->d_film) LJ_CUDA(cudaMalloc(&s->d_film, (size_t)npix * 16));
     if (d_var && !s->d_film_sq) LJ_CUDA(cudaMalloc(&s->d_film_sq, (size_t)npix * 16));
@@ -337,16 +417,18 @@ static int render_impl(lj_scene *s, const lj_render_opts *opts_in, float *d_out,
 
     const int nb256 = (capacity + 255) / 256, nb128 = (capacity + 127) / 128;
     // persistent grid: exactly one wave of resident CTAs (SM count x the occupancy of k_trace)
-    static int trace_blocks = 0;
+    static int trace_blocks = 0, walk_blocks = 1;
     if (trace_blocks == 0) {
 #if defined(LJ_HOSTSIM)
         trace_blocks = 1;
 #else
-        int sms = 0, a0 = 0, a1 = 0;
+        int sms = 0, a0 = 0, a1 = 0, a2 = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a0, k_trace<false>, 128, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a1, k_trace<true>, 128, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a0, k_trace<0>, 128, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a1, k_trace<1>, 128, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a2, k_trace<2>, 128, 0);
         trace_blocks = std::max(1, sms) * std::max(1, std::min(a0, a1));
+        walk_blocks = std::max(1, sms) * std::max(1, a2);
 #endif
     }
     unsigned int *d_cursors = nullptr;
@@ -386,16 +468,19 @@ static int render_impl(lj_scene *s, const lj_render_opts *opts_in, float *d_out,
             if (h_active[w % kRing] == 0) { waves = w; marks.push_back(e0); marks.push_back(e1); marks.push_back(nullptr); break; }
         }
         LJ_CUDA(cudaMemsetAsync(d_cursors, 0, 2 * sizeof(unsigned int), stream));
-        LJ_LAUNCH(k_trace<false>, trace_blocks, 128, stream, sc, a);
+        LJ_LAUNCH(k_trace<0>, trace_blocks, 128, stream, sc, a);
         LJ_CUDA(cudaEventRecord(e2, stream));
-        switch (shade_occ) {
+        if (vol) {
+            LJ_LAUNCH(k_shade_vol, nb128, 128, stream, sc, a);
+        } else switch (shade_occ) {
             case 5: LJ_LAUNCH(k_shade<5>, nb128, 128, stream, sc, a); break;
             case 6: LJ_LAUNCH(k_shade<6>, nb128, 128, stream, sc, a); break;
             case 8: LJ_LAUNCH(k_shade<8>, nb128, 128, stream, sc, a); break;
             default: LJ_LAUNCH(k_shade<4>, nb128, 128, stream, sc, a); break;
         }
         LJ_CUDA(cudaEventRecord(e3, stream));
-        LJ_LAUNCH(k_trace<true>, trace_blocks, 128, stream, sc, a);
+        if (vol) LJ_LAUNCH(k_trace<2>, walk_blocks, 128, stream, sc, a);
+        else LJ_LAUNCH(k_trace<1>, trace_blocks, 128, stream, sc, a);
         LJ_CUDA(cudaEventRecord(e4, stream));
         launches += 3;
         queued++;

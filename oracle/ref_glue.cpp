@@ -352,6 +352,32 @@ void ljo_light(void *h, const lj_light_query *q, int64_t n, lj_light_result *out
         out[i] = r;
     }
 }
+// medium.h:25-31 / phase_function.h:18-29 on the reference's own objects (see lj_medium_batch)
+void ljo_medium(void *h, const lj_medium_query *q, int64_t n, lj_medium_result *out) {
+    const Scene &s = *(const Scene *)h;
+    for (int64_t i = 0; i < n; i++) {
+        const Medium &m = s.media[q[i].medium_id];
+        Vector3 o{q[i].org[0], q[i].org[1], q[i].org[2]}, d{q[i].dir[0], q[i].dir[1], q[i].dir[2]};
+        Ray ray{o, d, Real(0), (Real)q[i].tfar};
+        Spectrum maj = get_majorant(m, ray);
+        Vector3 p = o + Real(q[i].t) * d;
+        Spectrum sa = get_sigma_a(m, p), ss = get_sigma_s(m, p);
+        PhaseFunction ph = get_phase_function(m);
+        lj_medium_result r;
+        memset(&r, 0, sizeof(r));
+        std::optional<Vector3> pd = sample_phase_function(ph, -d, Vector2{q[i].rnd[0], q[i].rnd[1]});
+        for (int c = 0; c < 3; c++) {
+            r.majorant[c] = (float)maj[c]; r.sigma_a[c] = (float)sa[c]; r.sigma_s[c] = (float)ss[c];
+            if (pd) r.phase_dir[c] = (float)(*pd)[c];
+        }
+        if (pd) {
+            r.phase_eval = (float)eval(ph, -d, *pd).x;
+            r.phase_pdf = (float)pdf_sample_phase(ph, -d, *pd);
+        }
+        out[i] = r;
+    }
+}
+int ljo_num_media(void *h) { return (int)((const Scene *)h)->media.size(); }
 void ljo_camera_rays(void *h, const float *xy, int64_t n, lj_ray *rays) {
     const Scene &s = *(const Scene *)h;
     for (int64_t i = 0; i < n; i++) {

@@ -39,6 +39,9 @@ def lib():
         l.ljo_intersect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         l.ljo_bsdf.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         l.ljo_light.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        l.ljo_medium.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        l.ljo_num_media.restype = C.c_int
+        l.ljo_num_media.argtypes = [C.c_void_p]
         l.ljo_camera_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         l.ljo_texture.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
         l.ljo_mip_level.restype = C.c_int
@@ -122,6 +125,15 @@ class RefScene:
         q = np.ascontiguousarray(queries, dtype=lj.LIGHT_QUERY_DTYPE)
         out = np.zeros(q.shape[0], dtype=lj.LIGHT_RESULT_DTYPE)
         lib().ljo_light(self.h, _p(q), q.shape[0], _p(out))
+        return out
+
+    def num_media(self):
+        return lib().ljo_num_media(self.h)
+
+    def medium(self, queries):
+        q = np.ascontiguousarray(queries, dtype=lj.MEDIUM_QUERY_DTYPE)
+        out = np.zeros(q.shape[0], dtype=lj.MEDIUM_RESULT_DTYPE)
+        lib().ljo_medium(self.h, _p(q), q.shape[0], _p(out))
         return out
 
     def sample_primary(self, screen_pos):

@@ -65,7 +65,8 @@ def test_vertex_camera_light_parity(oracle, name):
     record("light_parity", dict(scene=name, **pc.check_light_parity(sc, ref, v["position"][v["shape_id"] >= 0])))
 
 
-@pytest.mark.parametrize("name", ["cbox", "veach_mi", "sponza", "matpreview"])
+@pytest.mark.parametrize("name", ["cbox", "veach_mi", "sponza", "matpreview", "disney_bsdf", "disney_glass", "disney_clearcoat",
+                                  "disney_sheen", "volpath_test5_2"])
 def test_bsdf_parity(oracle, name):
     """Parity test 2 of north_star: BSDF eval / pdf / sample on fixed inputs."""
     sc, ref = pair(oracle, name)
@@ -127,6 +128,57 @@ def test_image_parity(oracle, name, spp):
     assert s["frac_z_gt_3"] <= 1.25 * null["frac_z_gt_3"] + 0.003, (s, null)
     assert s["block_frac_z_gt_4"] <= null["block_frac_z_gt_4"] + 0.002, (s, null)
     assert s["block_z_rms"] <= 1.15 * null["block_z_rms"], (s, null)
+
+
+@pytest.mark.parametrize("name", ["volpath_test6", "hetvol", "hetvol_colored", "vol_cbox_teapot"])
+def test_medium_parity(oracle, name):
+    sc, ref = pair(oracle, name)
+    record("medium_parity", dict(scene=name, media=pc.check_medium_parity(sc, ref)))
+
+
+def test_light_parity_facing_the_pole(oracle):
+    """See tests/test_hostsim.py: sphere-light sampling frames around -z (lj_common.h coordinate_system)."""
+    sc, ref = pair(oracle, "volpath_test5_2")
+    rays = ref.sample_primary((0.45 + 0.1 * np.random.default_rng(11).random((1 << 15, 2))).astype(np.float32))
+    v = ref.intersect(rays)
+    record("light_parity", dict(scene="volpath_test5_2", **pc.check_light_parity(sc, ref, v["position"][v["shape_id"] >= 0])))
+
+
+# Configs 3 and 5 of BASELINE.json.  The public reference ships these estimators as homework stubs; the image on the
+# CPU side comes from the reference renderer with OUR handout restatement linked in (oracle/overlay, "lajolla_ref_hw"):
+# PARITY UNPINNED by any reference code -- what this checks is device code == CPU restatement of the same handout.
+@pytest.mark.parametrize("name,spp", [("disney_bsdf", 64), ("disney_glass", 32), ("disney_metal", 32),
+                                      ("volpath_test4_2", 32), ("volpath_test5_2", 32), ("volpath_test6", 64), ("vol_cbox_teapot", 16),
+                                      ("hetvol", 16), ("hetvol_colored", 16)])
+def test_image_parity_homework_configs(oracle, name, spp):
+    """Same null-calibrated statistics as test_image_parity (image mean within 1.5 %, tail fractions of the pixel
+    and 8x8-tile z statistics no worse than what two device renders with different seeds give each other)."""
+    sc, ref = pair(oracle, name)
+    img, var = sc.render(spp=spp, variance=True)
+    st = sc.last_stats
+    img_b, _ = sc.render(spp=spp, variance=True, seed=0x5eed5eed5eed)
+    h, w = img.shape[:2]
+    assert st.samples == w * h * spp
+    ref_img, secs = ref.render(spp=spp)
+    null = pc.image_stats(img_b, img, var, var)
+    s = pc.image_stats(img, ref_img, var, var)
+    record("image_parity_hw", dict(scene=name, spp=spp, gpu_ms=st.render_ms, ref_s=secs, **s,
+                                   null={k: null[k] for k in ("relmse", "frac_z_gt_3", "block_frac_z_gt_4", "block_z_rms")},
+                                   gpu_msamples=st.samples / st.render_ms / 1e3, ref_msamples=w * h * spp / secs / 1e6,
+                                   rays=st.closest_rays + st.shadow_rays, bounces=st.bounces, waves=st.waves))
+    np.save(os.path.join(OUT, f"img_{name}_gpu.npy"), img.astype(np.float16))
+    np.save(os.path.join(OUT, f"img_{name}_ref.npy"), ref_img.astype(np.float16))
+    assert np.all(np.isfinite(img))
+    # The one-sample lobe mixture of homework1.tex has unbounded f / pdf where a direction sampled from one lobe lies
+    # under the shading horizon (|n.w| in eval, max(n.w, 0) in the cosine pdf): single samples of 1e7 occur on both
+    # sides (same f and pdf to 1e-4 in the oracle).  The mean is therefore compared on images clipped at 20x the
+    # reference mean, which changes both expectations alike.
+    clip = 20 * float(np.mean(ref_img))
+    m_gpu, m_ref = np.minimum(img, clip).mean(axis=(0, 1)), np.minimum(ref_img, clip).mean(axis=(0, 1))
+    assert np.allclose(m_gpu, m_ref, rtol=0.015), (m_gpu, m_ref, s)
+    assert s["frac_z_gt_3"] <= 1.25 * null["frac_z_gt_3"] + 0.003, (s, null)
+    assert s["block_frac_z_gt_4"] <= null["block_frac_z_gt_4"] + 0.003, (s, null)
+    assert s["block_z_rms"] <= 1.15 * null["block_z_rms"] + 0.02, (s, null)
 
 
 def test_sample_range_split_is_additive(oracle):
