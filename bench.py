@@ -31,7 +31,13 @@ WORKLOADS = {
     "sponza": ("sponza", 1024, 4),
     "cbox": ("cbox", 64, 8),
     "veach_mi": ("veach_mi", 256, 8),
+    "disney_bsdf": ("disney_bsdf", 256, 4),
+    "volpath_test6": ("volpath_test6", 1024, 4),
+    "hetvol": ("hetvol", 1024, 1),
+    "hetvol_colored": ("hetvol_colored", 1024, 1),
+    "vol_cbox_teapot": ("vol_cbox_teapot", 1024, 2),
 }
+VOLPATH = {"volpath_test6", "hetvol", "hetvol_colored", "vol_cbox_teapot"}
 BYTES_PER_EXTENSION_RAY = 104  # 2R + 2H, R = 32 B ray, H = 20 B hit
 
 
@@ -129,12 +135,12 @@ def run_reference(args):
     total = sum(s for s, _ in secs)
     value = w * h * spp * len(secs) / total / 1e6
     mrays = sum(r for _, r in secs) / total / 1e6
-    sample = f"{key} {w}x{h} at {spp} spp per step (Msamples/s is spp-invariant), lajolla+shim"
+    sample = f"{key} {w}x{h} at {spp} spp per step (Msamples/s is spp-invariant), lajolla+shim" + (" + handout overlay (lajolla_ref_hw)" if key in VOLPATH or key.startswith("disney") else "")
     line = {
         "impl": "reference", "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(secs), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{key} {w}x{h} path integrator, {full_spp} spp (timed on a {spp} spp sample)"},
+        "config": {"workload": f"{key} {w}x{h} {'volpath' if key in VOLPATH else 'path'} integrator, {full_spp} spp (timed on a {spp} spp sample)"},
         "mrays_per_s": mrays,
         "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -184,7 +190,8 @@ def main():
     npix = w * h
     total_spp = spp * world
     film = torch.zeros((h, w, 3), dtype=torch.float32, device="cuda")
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()  # a non-blocking stream of our own: the legacy default stream serialises against every other stream
+    torch.cuda.set_stream(stream)
 
     def step():
         # every rank renders its own spp block of the (spp * world)-sample image
@@ -250,8 +257,8 @@ def main():
             "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{key} {w}x{h} path integrator, {spp} spp per GPU ({total_spp} spp image)",
-                       "l2_policy": "path pool (4M slots x 144 B = 604 MB) streams through HBM every wave, larger than the 126 MB L2",
+            "config": {"workload": f"{key} {w}x{h} {'volpath' if key in VOLPATH else 'path'} integrator, {spp} spp per GPU ({total_spp} spp image)",
+                       "l2_policy": f"path pool (4M slots x {224 if key in VOLPATH else 144} B) streams through HBM every wave, larger than the 126 MB L2",
                        "scene_source": "reference scene flattened to .ljs", "parallelism": f"spp-split x{world} + NCCL reduce"},
             "mrays_per_s": (agg["closest"] + agg["shadow"]) * world / (ms_total / 1e3) / 1e6,
             "rays_per_sample": (agg["closest"] + agg["shadow"]) / max(agg["samples"], 1),

@@ -127,6 +127,10 @@ extern "C" void lj_scene_destroy(lj_scene *s) {
     if (s->pool_block) cudaFree(s->pool_block);
     if (s->d_film) cudaFree(s->d_film);
     if (s->d_film_sq) cudaFree(s->d_film_sq);
+    for (cudaEvent_t e : s->event_pool) cudaEventDestroy(e);
+    if (s->d_counters) cudaFree(s->d_counters);
+    if (s->d_cursors) cudaFree(s->d_cursors);
+    if (s->h_counters) cudaFreeHost(s->h_counters);
     for (auto &e : s->ev) if (e) cudaEventDestroy(e);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;

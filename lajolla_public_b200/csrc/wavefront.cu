@@ -349,14 +349,14 @@ static int ensure_pool(lj_scene *s, int capacity, bool vol) {
     return LJ_OK;
 }
 
-struct EventPool {
-    std::vector<cudaEvent_t> ev;
+struct EventPool {  // hands out the scene's events in order; they live until lj_scene_destroy
+    std::vector<cudaEvent_t> &ev;
     size_t used = 0;
+    explicit EventPool(std::vector<cudaEvent_t> &pool) : ev(pool) {}
     cudaEvent_t next() {
         if (used == ev.size()) { cudaEvent_t e; cudaEventCreate(&e); ev.push_back(e); }
         return ev[used++];
     }
-    ~EventPool() { for (auto e : ev) cudaEventDestroy(e); }
 };
 
 static int render_impl(lj_scene *s, const lj_render_opts *opts_in, float *d_out, float *d_var, cudaStream_t stream, lj_stats *stats) {
@@ -388,10 +388,11 @@ static int render_impl(lj_scene *s, const lj_render_opts *opts_in, float *d_out,
     if (r != LJ_OK) return r;
     if (!s->d_film) LJ_CUDA(cudaMalloc(&s->d_film, (size_t)npix * 16));
     if (d_var && !s->d_film_sq) LJ_CUDA(cudaMalloc(&s->d_film_sq, (size_t)npix * 16));
-    unsigned long long *d_counters = nullptr;
-    LJ_CUDA(cudaMalloc(&d_counters, sizeof(unsigned long long) * C_COUNT));
-    unsigned long long *h_counters = nullptr;  // C_COUNT final counters, then the ring of per-wave live-path counts
-    LJ_CUDA(cudaMallocHost(&h_counters, sizeof(unsigned long long) * (C_COUNT + 8)));
+    if (!s->d_counters) LJ_CUDA(cudaMalloc(&s->d_counters, sizeof(unsigned long long) * C_COUNT));
+    if (!s->h_counters) LJ_CUDA(cudaMallocHost(&s->h_counters, sizeof(unsigned long long) * (C_COUNT + 8)));
+    if (!s->d_cursors) LJ_CUDA(cudaMalloc(&s->d_cursors, 2 * sizeof(unsigned int)));
+    unsigned long long *d_counters = s->d_counters;
+    unsigned long long *h_counters = s->h_counters;  // C_COUNT final counters, then the ring of per-wave live-path counts
     unsigned long long *h_active = h_counters + C_COUNT;
 
     WaveArgs a;
@@ -431,10 +432,9 @@ static int render_impl(lj_scene *s, const lj_render_opts *opts_in, float *d_out,
         walk_blocks = std::max(1, sms) * std::max(1, a2);
 #endif
     }
-    unsigned int *d_cursors = nullptr;
-    LJ_CUDA(cudaMalloc(&d_cursors, 2 * sizeof(unsigned int)));
+    unsigned int *d_cursors = s->d_cursors;
     a.cursors = d_cursors;
-    EventPool evp;
+    EventPool evp(s->event_pool);
     std::vector<cudaEvent_t> marks;  // 5 per wave: before regen, extend, shade, shadow, after shadow
     uint64_t launches = 0, waves = 0;
 
@@ -521,9 +521,6 @@ static int render_impl(lj_scene *s, const lj_render_opts *opts_in, float *d_out,
         stats->extend_launches = stats->shade_launches = stats->shadow_launches = waves;
         stats->regen_launches = waves + 1;
     }
-    cudaFree(d_counters);
-    cudaFree(d_cursors);
-    cudaFreeHost(h_counters);
     return LJ_OK;
 }
 
