@@ -193,12 +193,14 @@ def main():
     stream = torch.cuda.Stream()  # a non-blocking stream of our own: the legacy default stream serialises against every other stream
     torch.cuda.set_stream(stream)
 
+    from lajolla_public_b200 import partition
+    _, s_begin, s_end = partition.weak_range(rank, world, spp)
+
     def step():
         # every rank renders its own spp block of the (spp * world)-sample image
-        st = scene.render_device(film.data_ptr(), stream.cuda_stream, spp=total_spp, sample_begin=rank * spp,
-                                 sample_end=(rank + 1) * spp, normalize=False, pool_paths=args.pool)
-        if dist is not None:
-            dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)  # the one collective
+        st = scene.render_device(film.data_ptr(), stream.cuda_stream, spp=total_spp, sample_begin=s_begin,
+                                 sample_end=s_end, normalize=False, pool_paths=args.pool)
+        partition.reduce_film(film, dist, 0)  # the one collective
         return st
 
     def barrier():

@@ -183,6 +183,29 @@ def test_image_parity_homework_configs(oracle, name, spp):
     assert s["block_z_rms"] <= 1.15 * null["block_z_rms"] + 0.02, (s, null)
 
 
+@pytest.mark.parametrize("name", ["cbox", "veach_mi", "matpreview", "disney_bsdf", "volpath_test6", "hetvol"])
+def test_golden_vectors(oracle, name):
+    """The CUDA kernels against the committed fixtures (tests/golden, answers of the reference's object code)."""
+    import golden_lib
+    sc, _ = pair(oracle, name)
+    g = golden_lib.GoldenScene(name)
+    record("golden", dict(scene=name, **golden_lib.run_checks(sc, g, name)))
+    assert g.calls >= 10
+
+
+def test_render_against_golden_tiles(oracle):
+    import golden_lib
+    z = np.load(golden_lib.GOLDEN_DIR + "/cbox_render.npz")
+    sc, _ = pair(oracle, "cbox")
+    img = sc.render(spp=64)
+    tiles = img.reshape(32, 16, 32, 16, 3).mean(axis=(1, 3))
+    gold = z["tiles"]
+    assert np.allclose(tiles.mean(axis=(0, 1)), gold.mean(axis=(0, 1)), rtol=0.01)
+    lum_t, lum_g = tiles.sum(axis=2), gold.sum(axis=2)
+    lit = lum_g > 0.05 * lum_g.mean()
+    assert np.median(np.abs(lum_t[lit] - lum_g[lit]) / lum_g[lit]) < 0.03
+
+
 def test_sample_range_split_is_additive(oracle):
     """Multi-GPU partition property: spp blocks rendered separately sum to the single render."""
     sc, _ = pair(oracle, "cbox")
