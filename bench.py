@@ -240,10 +240,17 @@ def main():
     e2e_steps = max(1, min(args.steps, 3))
     barrier()
     t0 = time.perf_counter()
+    e2e_parts = {"create_s": 0.0, "render_s": 0.0, "close_s": 0.0, "device_render_ms": 0.0}
     for _ in range(e2e_steps):
+        ta = time.perf_counter()
         sc2 = lj.Scene(desc, device=local_rank)
+        tb = time.perf_counter()
         img = sc2.render(spp=total_spp, sample_begin=rank * spp, sample_end=(rank + 1) * spp, normalize=True, pool_paths=args.pool)
+        tc = time.perf_counter()
+        e2e_parts["device_render_ms"] += sc2.last_stats.render_ms / e2e_steps
         sc2.close()
+        td = time.perf_counter()
+        e2e_parts["create_s"] += (tb - ta) / e2e_steps; e2e_parts["render_s"] += (tc - tb) / e2e_steps; e2e_parts["close_s"] += (td - tc) / e2e_steps
     torch.cuda.synchronize()
     e2e_s = torch.tensor([time.perf_counter() - t0], device="cuda")
     if dist is not None:
@@ -270,7 +277,7 @@ def main():
             "stage_ms_per_step": {k: agg[k] / args.steps for k in ("regen_ms", "extend_ms", "shade_ms", "shadow_ms", "render_ms")},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": int(cdesc_bytes),
-                    "d2h_bytes_per_step": int(npix * 3 * 4), "includes": "lj_scene_create (upload + GPU BVH/mip build) + lj_render + D2H"},
+                    "d2h_bytes_per_step": int(npix * 3 * 4), "includes": "lj_scene_create (upload + GPU BVH/mip build) + lj_render + D2H", "parts": e2e_parts},
             "gpu_launches": int(agg["launches"]),
             "roofline": {"bound": "hbm", "kernel": "k_extend", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,

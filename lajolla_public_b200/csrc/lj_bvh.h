@@ -131,8 +131,9 @@ LJ_HD float refine_hit_t(const DevPrim *prims, int prim, V3 o, V3 d, float t32) 
 // slots (lj_bvh_build.h) and the bit of slot s is 24 + (s ^ octinv), so front-to-back order comes
 // from the ray's sign octant alone and no distances are sorted.  Written as resumable steps so the
 // persistent kernels (wavefront.cu) can interleave traversal with fetching new rays into idle lanes.
-// Edge-tie policy: a later candidate replaces the current hit only if strictly
-// nearer, so among exactly equal t the first one visited wins.
+// Edge-tie policy (same as oracle/embree_shim.cpp): among candidates with exactly equal t the lowest
+// (shape id, primitive id) wins -- independent of visiting order, which in the persistent kernels depends on
+// which other rays share the warp (a ray through a shared edge would otherwise shade differently run to run).
 constexpr int kStack8 = 48;         // entries; node groups need <= tree depth (checked at build, <= 30)
 constexpr int kTriPostponeMax = 16; // primitive groups are postponed only below this fill level
 
@@ -270,6 +271,12 @@ LJ_HD void trav_node(const DevNode8 *nodes, Trav &tr) {
     tr.Gt.y = hitmask & 0x00ffffffu;
 }
 
+LJ_HD bool prim_tie_less(const DevPrim *prims, int a, int b) {
+    V4 ca = ld4(&prims[a].c), cb = ld4(&prims[b].c);
+    int sa = prim_shape_id(ca), sb = prim_shape_id(cb);
+    return sa != sb ? sa < sb : prim_primitive_id(ca) < prim_primitive_id(cb);
+}
+
 // Test ONE primitive of group tr.Gt (highest bit first).  ANY: returns true at the first hit.
 template <bool ANY>
 LJ_HD bool trav_prim(const DevPrim *prims, Trav &tr) {
@@ -280,6 +287,7 @@ LJ_HD bool trav_prim(const DevPrim *prims, Trav &tr) {
     if (hit_prim(prims, idx, tr.o, tr.d, tr.tnear, tr.hit.t, t)) {
         if (ANY) { tr.hit.prim = idx; tr.hit.t = t; return true; }
         if (t < tr.hit.t || tr.hit.prim == kNoHit) { tr.hit.t = t; tr.hit.prim = idx; }
+        else if (t == tr.hit.t && prim_tie_less(prims, idx, tr.hit.prim)) tr.hit.prim = idx;
     }
     return false;
 }

@@ -22,6 +22,11 @@
 namespace lj {
 
 enum { C_SAMPLES = 0, C_CLOSEST, C_SHADOW, C_BOUNCES, C_ACTIVE, C_NEXT, C_NODE_STEPS, C_PRIM_TESTS, C_COUNT };
+// Statistics counters every warp of a full-pool kernel adds to are striped over kStripes addresses (folded on the
+// host): 131k same-address reductions per launch serialise in one L2 slice otherwise.
+constexpr int kStripes = 64;
+constexpr int C_BOUNCES_STRIPED = C_COUNT;               // kStripes entries
+constexpr int C_TOTAL = C_COUNT + kStripes;
 
 struct WaveArgs {
     PathPool pool;
@@ -33,11 +38,21 @@ struct WaveArgs {
     unsigned long long total_items;  // padded pixels * samples in this call
     int tiles_x, tiles_y;
     int prim_min_lanes, refill_threshold;  // scheduling policy of k_trace
+    int chunk;                             // slots a warp takes from the cursor at a time
 };
 
 __device__ __forceinline__ void warp_add(unsigned long long *ctr, unsigned v) {
     unsigned s = __reduce_add_sync(0xffffffffu, v);
     if (LJ_LANE() == 0 && s) atomicAdd(ctr, (unsigned long long)s);
+}
+
+// One 16-byte reduction per finished sample (red.global.add.v4.f32, sm_90+) instead of four scalar atomics.
+__device__ __forceinline__ void film_add(float *px, float r, float g, float b, float n) {
+#if defined(__CUDA_ARCH__)
+    atomicAdd(reinterpret_cast<float4 *>(px), make_float4(r, g, b, n));
+#else
+    px[0] += r; px[1] += g; px[2] += b; px[3] += n;
+#endif
 }
 
 // K1 + K7.  Work item k -> (sample, 8x4 pixel tile, lane) so one warp starts 32 neighbouring pixels.
@@ -58,24 +73,33 @@ __global__ void __launch_bounds__(256) k_regen(const LJ_GRID_CONSTANT DevScene s
         // K7: accumulate the finished sample (render.cpp:92) -- non-finite samples are dropped
         V4 r = a.pool.rad[i];
         if (is_finite(r.x) && is_finite(r.y) && is_finite(r.z)) {
-            float *px = a.film + 4 * (size_t)pixel;
-            atomicAdd(px + 0, r.x); atomicAdd(px + 1, r.y); atomicAdd(px + 2, r.z); atomicAdd(px + 3, 1.f);
-            if (a.film_sq) {
-                float *sq = a.film_sq + 4 * (size_t)pixel;
-                atomicAdd(sq + 0, r.x * r.x); atomicAdd(sq + 1, r.y * r.y); atomicAdd(sq + 2, r.z * r.z);
-            }
+            film_add(a.film + 4 * (size_t)pixel, r.x, r.y, r.z, 1.f);
+            if (a.film_sq) film_add(a.film_sq + 4 * (size_t)pixel, r.x * r.x, r.y * r.y, r.z * r.z, 0.f);
         }
         finished = 1;
     }
-    // warp-aggregated grab of the next work items
     unsigned mask = __ballot_sync(0xffffffffu, need);
-    unsigned long long base = 0;
-    int lane = LJ_LANE();
-    if (mask) {
-        int leader = __ffs(mask) - 1;
-        if (lane == leader) base = atomicAdd(&a.counters[C_NEXT], (unsigned long long)__popc(mask));
-        base = __shfl_sync(0xffffffffu, base, leader);
+    const int lane = LJ_LANE();
+#if defined(LJ_HOSTSIM)  // serial stand-in: "warps" of one thread, no block to cooperate with
+    unsigned long long base = need ? atomicAdd(&a.counters[C_NEXT], 1ull) : 0ull;
+#else
+    // block-aggregated grab of the next work items: one returning atomic per 256 slots (a per-warp atomic on the
+    // one cursor costs ~0.4 ms per wave in same-address serialisation)
+    __shared__ unsigned s_warp_need[8];
+    __shared__ unsigned long long s_base;
+    __shared__ unsigned s_cnt[2];
+    const int warp = threadIdx.x >> 5;
+    if (lane == 0) s_warp_need[warp] = __popc(mask);
+    if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned tot = 0;
+        for (int k = 0; k < 8; k++) { unsigned c = s_warp_need[k]; s_warp_need[k] = tot; tot += c; }
+        s_base = tot ? atomicAdd(&a.counters[C_NEXT], (unsigned long long)tot) : 0ull;
     }
+    __syncthreads();
+    unsigned long long base = s_base + s_warp_need[warp];
+#endif
     unsigned started = 0;
     if (need) {
         unsigned long long k = base + __popc(mask & ((1u << lane) - 1));
@@ -101,8 +125,19 @@ __global__ void __launch_bounds__(256) k_regen(const LJ_GRID_CONSTANT DevScene s
             a.pool.sh_d[i] = mk4(0, 0, 0, -1.f);
         }
     }
+#if defined(LJ_HOSTSIM)
     warp_add(&a.counters[C_SAMPLES], finished);
     warp_add(&a.counters[C_ACTIVE], started + (alive ? 1u : 0u));
+#else
+    // statistics: block totals through shared memory, one reduction per block and counter
+    unsigned f = __reduce_add_sync(0xffffffffu, finished), l = __reduce_add_sync(0xffffffffu, started + (alive ? 1u : 0u));
+    if (lane == 0) { if (f) atomicAdd(&s_cnt[0], f); if (l) atomicAdd(&s_cnt[1], l); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_cnt[0]) atomicAdd(&a.counters[C_SAMPLES], (unsigned long long)s_cnt[0]);
+        if (s_cnt[1]) atomicAdd(&a.counters[C_ACTIVE], (unsigned long long)s_cnt[1]);
+    }
+#endif
 }
 
 // K2 / K3: persistent-thread traversal over the path pool.  Each warp takes 32 consecutive slots at a
@@ -133,19 +168,33 @@ __global__ void __launch_bounds__(128) k_trace(const LJ_GRID_CONSTANT DevScene s
     trav_terminate(tr);
     int slot = -1;
     bool has_ray = false;
-    bool drained = false;  // warp-uniform: the cursor ran past the pool
+    bool drained = false;  // warp-uniform: the cursor ran past the pool and the warp's own run is used up
+    bool global_out = false;
+    unsigned chunk_next = 0, chunk_end = 0;
+    const unsigned chunk = (unsigned)a.chunk;
     unsigned traced = 0, node_steps = 0, prim_tests = 0;
     for (;;) {
-        // ---- fetch: lanes without a ray take the next slots
+        // ---- fetch: lanes without a ray take the next slots.  The warp owns a private run of slots [chunk_next,
+        // chunk_end) and goes to the global cursor only when that runs out: one same-address atomic per a.chunk
+        // slots instead of one per refill.
         unsigned want = drained ? 0u : __ballot_sync(0xffffffffu, !has_ray);
         if (want) {
-            int leader = __ffs(want) - 1;
-            unsigned base = 0;
-            if (lane == leader) base = atomicAdd(cursor, (unsigned)__popc(want));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            drained = base + (unsigned)__popc(want) >= n;
+            const unsigned cnt = (unsigned)__popc(want);
+            const unsigned lim = chunk_end < n ? chunk_end : n;
+            const unsigned left = chunk_next < lim ? lim - chunk_next : 0u;
+            unsigned nb = 0;
+            bool fresh = false;
+            if (cnt > left && !global_out) {
+                if (lane == 0) nb = atomicAdd(cursor, chunk);
+                nb = __shfl_sync(0xffffffffu, nb, 0);
+                if (nb >= n) global_out = true; else fresh = true;
+            }
+            const unsigned rank = (unsigned)__popc(want & ((1u << lane) - 1));
+            const unsigned idx = rank < left ? chunk_next + rank : (fresh ? nb + (rank - left) : 0xffffffffu);
+            if (fresh) { chunk_next = nb + (cnt - left); chunk_end = nb + chunk; }
+            else chunk_next += cnt < left ? cnt : left;
+            drained = global_out && chunk_next >= (chunk_end < n ? chunk_end : n);
             if (!has_ray) {
-                unsigned idx = base + __popc(want & ((1u << lane) - 1));
                 if (idx < n) {
                     slot = (int)idx;
                     if (WALK) {
@@ -282,7 +331,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_shade(const LJ_GRID_CONSTAN
             store_state(a.pool, i, s, (s.flags & kAlive) != 0);
         }
     }
-    warp_add(&a.counters[C_BOUNCES], cnt.bounces);
+    warp_add(&a.counters[C_BOUNCES_STRIPED + ((blockIdx.x * 4 + (threadIdx.x >> 5)) & (kStripes - 1))], cnt.bounces);
 }
 
 // K4 + K5 for the volpath integrator (lj_volpath.h)
@@ -298,7 +347,7 @@ __global__ void __launch_bounds__(128) k_shade_vol(const LJ_GRID_CONSTANT DevSce
             store_state_vol(a.pool, i, s, (s.flags & kAlive) != 0);
         }
     }
-    warp_add(&a.counters[C_BOUNCES], cnt.bounces);
+    warp_add(&a.counters[C_BOUNCES_STRIPED + ((blockIdx.x * 4 + (threadIdx.x >> 5)) & (kStripes - 1))], cnt.bounces);
 }
 
 __global__ void k_clear_pool(PathPool pool) {
@@ -388,12 +437,12 @@ static int render_impl(lj_scene *s, const lj_render_opts *opts_in, float *d_out,
     if (r != LJ_OK) return r;
     if (!s->d_film) LJ_CUDA(cudaMalloc(&s->d_film, (size_t)npix * 16));
     if (d_var && !s->d_film_sq) LJ_CUDA(cudaMalloc(&s->d_film_sq, (size_t)npix * 16));
-    if (!s->d_counters) LJ_CUDA(cudaMalloc(&s->d_counters, sizeof(unsigned long long) * C_COUNT));
-    if (!s->h_counters) LJ_CUDA(cudaMallocHost(&s->h_counters, sizeof(unsigned long long) * (C_COUNT + 8)));
+    if (!s->d_counters) LJ_CUDA(cudaMalloc(&s->d_counters, sizeof(unsigned long long) * C_TOTAL));
+    if (!s->h_counters) LJ_CUDA(cudaMallocHost(&s->h_counters, sizeof(unsigned long long) * (C_TOTAL + 8)));
     if (!s->d_cursors) LJ_CUDA(cudaMalloc(&s->d_cursors, 2 * sizeof(unsigned int)));
     unsigned long long *d_counters = s->d_counters;
     unsigned long long *h_counters = s->h_counters;  // C_COUNT final counters, then the ring of per-wave live-path counts
-    unsigned long long *h_active = h_counters + C_COUNT;
+    unsigned long long *h_active = h_counters + C_TOTAL;
 
     WaveArgs a;
     a.pool = s->pool;
@@ -413,6 +462,8 @@ static int render_impl(lj_scene *s, const lj_render_opts *opts_in, float *d_out,
     a.refill_threshold = kRefillThreshold;
     if (const char *e = getenv("LJ_PRIM_MIN_LANES")) a.prim_min_lanes = atoi(e);
     if (const char *e = getenv("LJ_REFILL")) a.refill_threshold = atoi(e);
+    a.chunk = 64;
+    if (const char *e = getenv("LJ_CHUNK")) a.chunk = std::max(32, atoi(e));
     int shade_occ = 4;  // resident CTAs per SM the shade kernel is compiled for (register cap), LJ_SHADE_OCC for tuning runs
     if (const char *e = getenv("LJ_SHADE_OCC")) shade_occ = atoi(e);
 
@@ -439,7 +490,7 @@ static int render_impl(lj_scene *s, const lj_render_opts *opts_in, float *d_out,
     uint64_t launches = 0, waves = 0;
 
     cudaEvent_t ev_begin = evp.next(), ev_end = evp.next();
-    LJ_CUDA(cudaMemsetAsync(d_counters, 0, sizeof(unsigned long long) * C_COUNT, stream));
+    LJ_CUDA(cudaMemsetAsync(d_counters, 0, sizeof(unsigned long long) * C_TOTAL, stream));
     LJ_CUDA(cudaMemsetAsync(s->d_film, 0, (size_t)npix * 16, stream));
     if (a.film_sq) LJ_CUDA(cudaMemsetAsync(s->d_film_sq, 0, (size_t)npix * 16, stream));
     LJ_CUDA(cudaEventRecord(ev_begin, stream));
@@ -490,7 +541,7 @@ static int render_impl(lj_scene *s, const lj_render_opts *opts_in, float *d_out,
     LJ_CUDA(cudaEventRecord(ev_end, stream));
     LJ_LAUNCH(k_resolve, (npix + 255) / 256, 256, stream, s->d_film, a.film_sq, npix, 1.f / (float)(se - sb), opts.normalize, d_out, d_var);
     launches++;
-    LJ_CUDA(cudaMemcpyAsync(h_counters, d_counters, sizeof(unsigned long long) * C_COUNT, cudaMemcpyDeviceToHost, stream));
+    LJ_CUDA(cudaMemcpyAsync(h_counters, d_counters, sizeof(unsigned long long) * C_TOTAL, cudaMemcpyDeviceToHost, stream));
     LJ_CUDA(cudaStreamSynchronize(stream));
     LJ_CUDA(cudaGetLastError());
     if (stats) {
@@ -514,6 +565,7 @@ static int render_impl(lj_scene *s, const lj_render_opts *opts_in, float *d_out,
         stats->closest_rays = h_counters[C_CLOSEST];
         stats->shadow_rays = h_counters[C_SHADOW];
         stats->bounces = h_counters[C_BOUNCES];
+        for (int k = 0; k < kStripes; k++) stats->bounces += h_counters[C_BOUNCES_STRIPED + k];
         stats->node_steps = h_counters[C_NODE_STEPS];
         stats->prim_tests = h_counters[C_PRIM_TESTS];
         stats->kernel_launches = launches;
