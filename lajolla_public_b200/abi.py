@@ -171,10 +171,11 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise ImportError(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+    path = os.environ.get("LJ_LIB", LIB_PATH)  # A/B builds of the CUDA library for tuning runs
+    if not os.path.exists(path):
+        raise ImportError(f"{path} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
                           "(nvcc, sm_100a). lajolla_public_b200 has no fallback implementation.")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     for name, (res, args) in PROTOTYPES.items():
         fn = getattr(lib, name)
         fn.restype = res

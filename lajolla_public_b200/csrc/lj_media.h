@@ -109,78 +109,104 @@ LJ_HD V3 tracking_exp(V3 majorant_minus_min, float t) {
 
 LJ_HD int tracking_channel(float u) { return clampi((int)(u * 3), 0, 2); }
 
-// homework2.tex:713-758.  Free flight over [0, t_hit] of the ray (o, d) by chromatic delta tracking.
+// The two tracking loops, cut into single collision steps so the persistent kernels (wavefront.cu k_flight,
+// k_trace<2>) can run ONE step per lane per warp iteration and refill lanes whose segment ended, instead of
+// letting 31 lanes wait for the longest loop (measured on hetvol: 4 of 32 lanes active otherwise).
+struct TrackState {
+    V3 majorant, maj_rel;  // maj_rel = majorant - min(majorant), see tracking_exp
+    float maj_c, max_maj;  // majorant of the sampled channel, max over channels
+    float accum_t;
+    int channel, it;
+};
+// Draws the channel.  Returns false when the sampled channel has no majorant (nothing to track).
+LJ_HD bool track_begin(const DevMedium &m, V3 o, V3 d, float ray_tfar, Pcg &rng, TrackState &ts) {
+    ts.majorant = medium_majorant(m, o, d, ray_tfar);
+    ts.channel = tracking_channel(pcg_uniform(rng));
+    ts.max_maj = max3(ts.majorant);
+    ts.maj_c = comp(ts.majorant, ts.channel);
+    ts.maj_rel = ts.majorant - mk3(min3(ts.majorant));
+    ts.accum_t = 0;
+    ts.it = 0;
+    return ts.maj_c > 0;
+}
+
+enum { kTrackContinue = 0, kTrackScatter = 1, kTrackEnd = 2 };
+
+// homework2.tex:713-758: one collision of the chromatic delta tracking free flight over [0, t_hit].
+LJ_HD int flight_step(const DevMedium &m, V3 o, V3 d, float t_hit, int max_null, Pcg &rng, TrackState &ts,
+                      V3 &transmittance, V3 &trans_dir_pdf, V3 &trans_nee_pdf) {
+    if (ts.it >= max_null) return kTrackEnd;
+    float t = -logf(1 - pcg_uniform(rng)) / ts.maj_c;
+    float dt = t_hit - ts.accum_t;
+    ts.accum_t = fminf(ts.accum_t + t, t_hit);
+    if (t < dt) {
+        V3 sa, ss;
+        medium_sigmas(m, o + d * ts.accum_t, sa, ss);
+        V3 sigma_t = sa + ss;
+        V3 real_prob = sigma_t / ts.majorant;
+        V3 e = tracking_exp(ts.maj_rel, t);
+        if (pcg_uniform(rng) < comp(real_prob, ts.channel)) {
+            transmittance *= e / ts.max_maj;
+            trans_dir_pdf *= e * ts.majorant * real_prob / ts.max_maj;
+            return kTrackScatter;
+        }
+        transmittance *= e * (ts.majorant - sigma_t) / ts.max_maj;
+        trans_dir_pdf *= e * ts.majorant * (mk3(1) - real_prob) / ts.max_maj;
+        trans_nee_pdf *= e * ts.majorant / ts.max_maj;
+        ts.it++;
+        return kTrackContinue;
+    }
+    V3 e = tracking_exp(ts.maj_rel, dt);
+    transmittance *= e;
+    trans_dir_pdf *= e;
+    trans_nee_pdf *= e;
+    return kTrackEnd;
+}
+
+// homework2.tex:771-810: one collision of ratio tracking over the shadow segment [0, next_t].
+LJ_HD int ratio_step(const DevMedium &m, V3 o, V3 d, float next_t, int max_null, Pcg &rng, TrackState &ts,
+                     V3 &T_light, V3 &p_trans_nee, V3 &p_trans_dir) {
+    if (ts.it >= max_null) return kTrackEnd;
+    float t = -logf(1 - pcg_uniform(rng)) / ts.maj_c;
+    float dt = next_t - ts.accum_t;
+    ts.accum_t = fminf(ts.accum_t + t, next_t);
+    if (t < dt) {
+        V3 sa, ss;
+        medium_sigmas(m, o + d * ts.accum_t, sa, ss);
+        V3 sigma_t = sa + ss;
+        V3 real_prob = sigma_t / ts.majorant;
+        V3 e = tracking_exp(ts.maj_rel, t);
+        T_light *= e * (ts.majorant - sigma_t) / ts.max_maj;
+        p_trans_nee *= e * ts.majorant / ts.max_maj;
+        p_trans_dir *= e * ts.majorant * (mk3(1) - real_prob) / ts.max_maj;
+        if (max3(T_light) <= 0) return kTrackEnd;
+        ts.it++;
+        return kTrackContinue;
+    }
+    V3 e = tracking_exp(ts.maj_rel, dt);
+    T_light *= e;
+    p_trans_nee *= e;
+    p_trans_dir *= e;
+    return kTrackEnd;
+}
+
+// Whole loops (query seam, host simulation, and anything that is not a persistent kernel).
 // Returns true on a real collision at distance accum_t; the three running products are updated in place.
 LJ_HD bool free_flight(const DevMedium &m, V3 o, V3 d, float ray_tfar, float t_hit, int max_null, Pcg &rng,
                        V3 &transmittance, V3 &trans_dir_pdf, V3 &trans_nee_pdf, float &accum_t) {
-    V3 majorant = medium_majorant(m, o, d, ray_tfar);
-    int channel = tracking_channel(pcg_uniform(rng));
-    float max_maj = max3(majorant);
-    float maj_c = comp(majorant, channel);
+    TrackState ts;
     accum_t = 0;
-    if (!(maj_c > 0)) return false;
-    const V3 maj_rel = majorant - mk3(min3(majorant));  // see tracking_exp
-    for (int it = 0; it < max_null; it++) {
-        float t = -logf(1 - pcg_uniform(rng)) / maj_c;
-        float dt = t_hit - accum_t;
-        accum_t = fminf(accum_t + t, t_hit);
-        if (t < dt) {
-            V3 sa, ss;
-            medium_sigmas(m, o + d * accum_t, sa, ss);
-            V3 sigma_t = sa + ss;
-            V3 real_prob = sigma_t / majorant;
-            V3 e = tracking_exp(maj_rel, t);
-            if (pcg_uniform(rng) < comp(real_prob, channel)) {
-                transmittance *= e / max_maj;
-                trans_dir_pdf *= e * majorant * real_prob / max_maj;
-                return true;
-            }
-            transmittance *= e * (majorant - sigma_t) / max_maj;
-            trans_dir_pdf *= e * majorant * (mk3(1) - real_prob) / max_maj;
-            trans_nee_pdf *= e * majorant / max_maj;
-        } else {
-            V3 e = tracking_exp(maj_rel, dt);
-            transmittance *= e;
-            trans_dir_pdf *= e;
-            trans_nee_pdf *= e;
-            return false;
-        }
-    }
-    return false;
+    if (!track_begin(m, o, d, ray_tfar, rng, ts)) return false;
+    int r;
+    do { r = flight_step(m, o, d, t_hit, max_null, rng, ts, transmittance, trans_dir_pdf, trans_nee_pdf); } while (r == kTrackContinue);
+    accum_t = ts.accum_t;
+    return r == kTrackScatter;
 }
-
-// homework2.tex:771-810.  Ratio tracking over one segment [0, next_t] of the shadow ray (o, d).
 LJ_HD void ratio_track(const DevMedium &m, V3 o, V3 d, float ray_tfar, float next_t, int max_null, Pcg &rng,
                        V3 &T_light, V3 &p_trans_nee, V3 &p_trans_dir) {
-    V3 majorant = medium_majorant(m, o, d, ray_tfar);
-    int channel = tracking_channel(pcg_uniform(rng));
-    float max_maj = max3(majorant);
-    float maj_c = comp(majorant, channel);
-    if (!(maj_c > 0)) return;
-    const V3 maj_rel = majorant - mk3(min3(majorant));
-    float accum_t = 0;
-    for (int it = 0; it < max_null; it++) {
-        float t = -logf(1 - pcg_uniform(rng)) / maj_c;
-        float dt = next_t - accum_t;
-        accum_t = fminf(accum_t + t, next_t);
-        if (t < dt) {
-            V3 sa, ss;
-            medium_sigmas(m, o + d * accum_t, sa, ss);
-            V3 sigma_t = sa + ss;
-            V3 real_prob = sigma_t / majorant;
-            V3 e = tracking_exp(maj_rel, t);
-            T_light *= e * (majorant - sigma_t) / max_maj;
-            p_trans_nee *= e * majorant / max_maj;
-            p_trans_dir *= e * majorant * (mk3(1) - real_prob) / max_maj;
-            if (max3(T_light) <= 0) return;
-        } else {
-            V3 e = tracking_exp(maj_rel, dt);
-            T_light *= e;
-            p_trans_nee *= e;
-            p_trans_dir *= e;
-            return;
-        }
-    }
+    TrackState ts;
+    if (!track_begin(m, o, d, ray_tfar, rng, ts)) return;
+    while (ratio_step(m, o, d, next_t, max_null, rng, ts, T_light, p_trans_nee, p_trans_dir) == kTrackContinue) {}
 }
 
 }  // namespace lj

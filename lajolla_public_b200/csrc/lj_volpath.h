@@ -23,6 +23,16 @@ LJ_HD int update_medium(int interior, int exterior, V3 dir, V3 geometric_normal,
 }
 
 constexpr uint32_t kWalkNoBudget = 0xffffu;
+constexpr int kScatter = -2;  // hit.prim of a path whose free flight ended in a real collision (hit.t = its distance)
+
+// Free flight of one path in whole-loop form (host simulation of k_flight and reference for its stepwise form):
+// updates throughput and the MIS caches, records a scattering event in s.hit.
+LJ_HD void flight_finish(PathState &s, bool scatter, float accum_t, V3 transmittance, V3 trans_dir_pdf, V3 trans_nee_pdf) {
+    s.T = s.T * transmittance / avg3(trans_dir_pdf);
+    s.mt_dir = s.mt_dir * trans_dir_pdf;
+    s.mt_nee = s.mt_nee * trans_nee_pdf;
+    if (scatter) { s.hit.t = accum_t; s.hit.u = 0; s.hit.v = 0; s.hit.prim = kScatter; }
+}
 
 // One shade step of the volumetric path tracer.  On return: s.flags has kAlive iff an extension ray was
 // written; s.sh_pdf_dir >= 0 iff an NEE walk was written.
@@ -33,20 +43,11 @@ LJ_HD void shade_vol_path(const DevScene &sc, const RenderParams &rp, PathState 
     const int bounces = (int)s.nv - 1;  // generate_path starts nv at 1
     s.sh_pdf_dir = -1;
     s.flags &= ~kAlive;
-    const bool has_hit = s.hit.prim != kNoHit;
-    const float t_hit = has_hit ? s.hit.t : LJ_INF;
-
-    // ---- free flight (:713-758) and throughput update (:814-816)
-    bool scatter = false;
-    float accum_t = 0;
-    V3 transmittance = mk3(1), trans_dir_pdf = mk3(1), trans_nee_pdf = mk3(1);
-    if (s.medium >= 0) {
-        scatter = free_flight(sc.media[s.medium], s.o, s.d, s.tfar, t_hit, sc.options.max_null_collisions, rng,
-                              transmittance, trans_dir_pdf, trans_nee_pdf, accum_t);
-    }
-    s.T = s.T * transmittance / avg3(trans_dir_pdf);
-    s.mt_dir = s.mt_dir * trans_dir_pdf;
-    s.mt_nee = s.mt_nee * trans_nee_pdf;
+    // The free flight over this ray (chromatic delta tracking, :713-758) and the throughput update (:814-816) were
+    // done by k_flight (flight_path below): a real collision is recorded as hit.prim == kScatter at distance hit.t.
+    const bool scatter = s.hit.prim == kScatter;
+    const bool has_hit = s.hit.prim >= 0;
+    const float accum_t = s.hit.t;
     if (!scatter && !has_hit) { cnt.finished++; s.rng_state = rng.state; return; }  // no envmaps in volpath (:196)
 
     Vertex vx;
@@ -229,17 +230,14 @@ LJ_HD void hit_medium_interface(const DevScene &sc, V3 org, V3 dir, const Hit &h
     }
 }
 
-// Consume the closest hit of the current segment.  Returns true when the walk is over; `contribution` is then
-// what the path's radiance gains (zero if blocked).
-LJ_HD bool nee_walk_step(const DevScene &sc, NeeWalk &w, const Hit &hit, float seg_tfar, V3 &contribution) {
+// Length of the segment just traversed (to the surface hit, or to the light point).
+LJ_HD float nee_walk_next_t(const NeeWalk &w, const Hit &hit) { return hit.prim != kNoHit ? hit.t : distance(w.pc, w.pl); }
+
+// After ratio tracking over the segment: opaque / index-matched test.  Returns true when the walk is over;
+// `contribution` is then what the path's radiance gains (zero if blocked).
+LJ_HD bool nee_walk_decide(const DevScene &sc, NeeWalk &w, const Hit &hit, V3 &contribution) {
     contribution = mk3(0);
-    const bool has_hit = hit.prim != kNoHit;
-    float next_t = has_hit ? hit.t : distance(w.pc, w.pl);
-    if (w.medium >= 0) {
-        ratio_track(sc.media[w.medium], w.pc, w.dir, seg_tfar, next_t, sc.options.max_null_collisions, w.rng,
-                    w.T_light, w.p_nee, w.p_dir);
-    }
-    if (has_hit) {
+    if (hit.prim != kNoHit) {
         V3 ng;
         int material_id, interior, exterior;
         hit_medium_interface(sc, w.pc, w.dir, hit, ng, material_id, interior, exterior);

@@ -451,6 +451,7 @@ extern "C" int lj_scene_create(const lj_scene_desc *desc, lj_scene **out) {
         m.phase_g = md.phase_g;
         for (int c = 0; c < 3; c++) { m.sigma_a[c] = md.sigma_a[c]; m.sigma_s[c] = md.sigma_s[c]; }
         if (md.type == LJ_MEDIUM_HETEROGENEOUS) {
+            s->has_grid_media = true;
             m.albedo = conv_volume(md.albedo, up);
             m.density = conv_volume(md.density, up);
         }

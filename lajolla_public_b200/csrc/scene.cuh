@@ -14,6 +14,7 @@ struct lj_scene {
     std::vector<void *> allocations;  // everything cudaMalloc'ed for this scene
     lj_scene_info info;
     int device = 0;
+    bool has_grid_media = false;  // some medium is heterogeneous: tracking loops run ~100 collisions per segment
     // host copies needed by introspection entry points
     std::vector<float> h_light_pmf, h_light_cdf;
     std::vector<lj::DevImage> h_images1, h_images3;

@@ -34,11 +34,12 @@ struct WaveArgs {
     unsigned long long *counters;  // C_COUNT
     float *film;                   // w*h*4: sum rgb, n
     float *film_sq;                // w*h*4: sum of squares rgb (may be null)
-    unsigned int *cursors;         // fetch cursors of the persistent trace kernels: [0] extend, [1] shadow
+    unsigned int *cursors;         // fetch cursors of the persistent kernels: [0] extend, [1] shadow / walk, [2] flight
     unsigned long long total_items;  // padded pixels * samples in this call
     int tiles_x, tiles_y;
     int prim_min_lanes, refill_threshold;  // scheduling policy of k_trace
     int chunk;                             // slots a warp takes from the cursor at a time
+    int track_refill;                      // k_flight / walk: refill once fewer lanes than this are tracking
 };
 
 __device__ __forceinline__ void warp_add(unsigned long long *ctr, unsigned v) {
@@ -149,6 +150,9 @@ __global__ void __launch_bounds__(256) k_regen(const LJ_GRID_CONSTANT DevScene s
 // they are postponed (pushed as a group) so the tests run with more of the warp active.
 // SHADOW = false: closest hit of pool.ray -> pool.hit.  SHADOW = true: any hit of the NEE segment; an
 // unoccluded segment adds its contribution to pool.rad.
+#ifndef LJ_WALK_MIN_BLOCKS
+#define LJ_WALK_MIN_BLOCKS 5
+#endif
 constexpr int kRefillThreshold = 20;  // defaults; LJ_REFILL / LJ_PRIM_MIN_LANES override them for tuning runs
 constexpr int kPrimMinLanes = 12;
 
@@ -156,11 +160,14 @@ constexpr int kPrimMinLanes = 12;
 // each segment is a closest-hit traversal, followed by ratio tracking over it and the index-matched / opaque test
 // (nee_walk_step); the walk's transmittance products stay in registers until the segment chain ends.
 template <int MODE>
-__global__ void __launch_bounds__(128) k_trace(const LJ_GRID_CONSTANT DevScene sc, const LJ_GRID_CONSTANT WaveArgs a) {
+__global__ void __launch_bounds__(128, MODE >= 2 ? LJ_WALK_MIN_BLOCKS : 1) k_trace(const LJ_GRID_CONSTANT DevScene sc, const LJ_GRID_CONSTANT WaveArgs a) {
     constexpr bool SHADOW = MODE == 1;
-    constexpr bool WALK = MODE == 2;
+    constexpr bool WALK = MODE >= 2;   // 2: whole ratio-tracking loop when a segment ends (homogeneous media: 1-2 collisions)
+    constexpr bool STEP = MODE == 3;   // 3: ratio tracking one collision per pass (heterogeneous media: ~100 per segment)
     NeeWalk wk;
-    float seg_tfar = 0;
+    TrackState ts;
+    float seg_tfar = 0, next_t = 0;
+    bool tracking = false;  // WALK: the lane is ratio tracking over the segment it just traversed
     const unsigned n = (unsigned)a.pool.capacity;
     unsigned int *cursor = &a.cursors[MODE == 0 ? 0 : 1];
     const int lane = LJ_LANE();
@@ -249,34 +256,79 @@ __global__ void __launch_bounds__(128) k_trace(const LJ_GRID_CONSTANT DevScene s
             const bool has_p = tr.Gt.y != 0;
             const bool work = !trav_done(tr);
             const unsigned wm = __ballot_sync(0xffffffffu, work);
-            if (wm == 0) break;
-            // refill once too few lanes are still traversing (never before the pass after a fetch made progress)
-            if (!first && !drained && __popc(wm) < a.refill_threshold) break;
-            const unsigned pm = __ballot_sync(0xffffffffu, has_p);
-            if (__popc(pm) >= a.prim_min_lanes || pm == wm) {
-                if (has_p) {
-                    prim_tests++;
-                    if (trav_prim<SHADOW>(sc.prims, tr)) trav_terminate(tr);  // any-hit ends at the first hit
+            // WALK: a lane is also busy while it tracks, or holds a traversed segment it has not looked at yet.  Each
+            // pass runs ONE of the two phases, the one more lanes are waiting for: traversal steps, or walk steps
+            // (segment end -> tracking step -> surface test -> next segment).
+            const unsigned km = STEP ? __ballot_sync(0xffffffffu, tracking || (has_ray && !work)) : 0u;
+            const unsigned busy = wm | km;
+            const bool trav_phase = !STEP || __popc(wm) >= __popc(km);
+            if (busy == 0) break;
+            // refill once too few lanes are still busy (never before the pass after a fetch made progress)
+            if (!first && !drained && __popc(busy) < (STEP ? a.track_refill : a.refill_threshold)) break;
+            if (wm && trav_phase) {
+                const unsigned pm = __ballot_sync(0xffffffffu, has_p);
+                if (__popc(pm) >= a.prim_min_lanes || pm == wm) {
+                    if (has_p) {
+                        prim_tests++;
+                        if (trav_prim<SHADOW>(sc.prims, tr)) trav_terminate(tr);  // any-hit ends at the first hit
+                    }
+                } else if (work) {
+                    bool descend = !has_p;
+                    if (has_p && tr.G.y != 0 && tr.sp < kTriPostponeMax) {
+                        tr.stack[tr.sp++] = tr.Gt;  // postpone these primitives, keep descending
+                        tr.Gt.y = 0;
+                        descend = true;
+                    }
+                    if (descend) {
+                        node_steps++;
+                        trav_node(sc.nodes8, tr);
+                    }
                 }
-            } else if (work) {
-                bool descend = !has_p;
-                if (has_p && tr.G.y != 0 && tr.sp < kTriPostponeMax) {
-                    tr.stack[tr.sp++] = tr.Gt;  // postpone these primitives, keep descending
-                    tr.Gt.y = 0;
-                    descend = true;
+                trav_next_group(tr);
+            }
+            if (STEP && !trav_phase) {
+                // A lane that finished traversing its segment starts tracking over it (or goes straight to the surface
+                // test) and takes its first collision step in the same pass; a tracking lane takes ONE collision step
+                // per pass (homework2.tex:771-810).  In homogeneous media a segment is over after one or two steps.
+                bool decide = false;
+                if (has_ray && !tracking && trav_done(tr)) {
+                    trav_finish_closest(sc.prims, tr);
+                    next_t = nee_walk_next_t(wk, tr.hit);
+                    if (wk.medium >= 0 && track_begin(sc.media[wk.medium], wk.pc, wk.dir, seg_tfar, wk.rng, ts)) tracking = true;
+                    else decide = true;
                 }
-                if (descend) {
-                    node_steps++;
-                    trav_node(sc.nodes8, tr);
+                if (tracking) {
+                    if (ratio_step(sc.media[wk.medium], wk.pc, wk.dir, next_t, sc.options.max_null_collisions, wk.rng, ts,
+                                   wk.T_light, wk.p_nee, wk.p_dir) != kTrackContinue) { tracking = false; decide = true; }
+                }
+                if (decide) {
+                    V3 contrib;
+                    if (nee_walk_decide(sc, wk, tr.hit, contrib)) {
+                        if (max3(contrib) > 0 || min3(contrib) < 0 || contrib.x != contrib.x || contrib.y != contrib.y || contrib.z != contrib.z) {
+                            V4 r = a.pool.rad[slot];
+                            a.pool.rad[slot] = mk4(r.x + contrib.x, r.y + contrib.y, r.z + contrib.z, r.w);
+                        }
+                        has_ray = false;
+                        trav_terminate(tr);
+                    } else {  // next segment of the same walk
+                        float tn;
+                        nee_walk_segment(sc, wk, tn, seg_tfar);
+                        trav_init(tr, wk.pc, wk.dir, tn, seg_tfar);
+                        traced++;
+                    }
                 }
             }
-            trav_next_group(tr);
         }
-        if (has_ray && trav_done(tr)) {  // finished (possibly in an earlier pass of this loop)
+        if (!STEP && has_ray && trav_done(tr)) {  // finished (possibly in an earlier pass of this loop)
             if (WALK) {
                 trav_finish_closest(sc.prims, tr);
+                next_t = nee_walk_next_t(wk, tr.hit);
+                if (wk.medium >= 0) {
+                    ratio_track(sc.media[wk.medium], wk.pc, wk.dir, seg_tfar, next_t, sc.options.max_null_collisions, wk.rng,
+                                wk.T_light, wk.p_nee, wk.p_dir);
+                }
                 V3 contrib;
-                if (nee_walk_step(sc, wk, tr.hit, seg_tfar, contrib)) {
+                if (nee_walk_decide(sc, wk, tr.hit, contrib)) {
                     if (max3(contrib) > 0 || min3(contrib) < 0 || contrib.x != contrib.x || contrib.y != contrib.y || contrib.z != contrib.z) {
                         V4 r = a.pool.rad[slot];
                         a.pool.rad[slot] = mk4(r.x + contrib.x, r.y + contrib.y, r.z + contrib.z, r.w);
@@ -332,6 +384,87 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_shade(const LJ_GRID_CONSTAN
         }
     }
     warp_add(&a.counters[C_BOUNCES_STRIPED + ((blockIdx.x * 4 + (threadIdx.x >> 5)) & (kStripes - 1))], cnt.bounces);
+}
+
+// K5: free flight of every live volpath ray by chromatic delta tracking (homework2.tex:713-758), persistent threads.
+// One warp iteration = ONE collision step for each lane that holds a path; lanes whose flight ended (real collision,
+// surface reached, or null-collision limit) write the result and are refilled from the cursor once fewer than
+// track_refill lanes are busy.  Result per path: thr *= transmittance / avg(trans_dir_pdf) (:814-816), the MIS caches
+// vol0 / vol1 *= the two pdf products (:521-558), rng state, and hit = (distance, kScatter) on a real collision.
+__global__ void __launch_bounds__(128) k_flight(const LJ_GRID_CONSTANT DevScene sc, const LJ_GRID_CONSTANT WaveArgs a) {
+    const unsigned n = (unsigned)a.pool.capacity;
+    unsigned int *cursor = &a.cursors[2];
+    const int lane = LJ_LANE();
+    const unsigned chunk = (unsigned)a.chunk;
+    unsigned chunk_next = 0, chunk_end = 0;
+    bool drained = false, global_out = false;
+    bool busy = false;
+    int slot = -1, medium = -1;
+    V3 o = mk3(0), d = mk3(0), tr = mk3(1), pd = mk3(1), pn = mk3(1);
+    float t_hit = 0;
+    Pcg rng;
+    rng.state = 0; rng.inc = 1;
+    TrackState ts;
+    for (;;) {
+        unsigned want = drained ? 0u : __ballot_sync(0xffffffffu, !busy);
+        if (want) {
+            const unsigned cnt = (unsigned)__popc(want);
+            const unsigned lim = chunk_end < n ? chunk_end : n;
+            const unsigned left = chunk_next < lim ? lim - chunk_next : 0u;
+            unsigned nb = 0;
+            bool fresh = false;
+            if (cnt > left && !global_out) {
+                if (lane == 0) nb = atomicAdd(cursor, chunk);
+                nb = __shfl_sync(0xffffffffu, nb, 0);
+                if (nb >= n) global_out = true; else fresh = true;
+            }
+            const unsigned rank = (unsigned)__popc(want & ((1u << lane) - 1));
+            const unsigned idx = rank < left ? chunk_next + rank : (fresh ? nb + (rank - left) : 0xffffffffu);
+            if (fresh) { chunk_next = nb + (cnt - left); chunk_end = nb + chunk; }
+            else chunk_next += cnt < left ? cnt : left;
+            drained = global_out && chunk_next >= (chunk_end < n ? chunk_end : n);
+            if (!busy && idx < n) {
+                V4 m = a.pool.meta[idx];
+                if (f2u(m.y) & kAlive) {
+                    V4 x = a.pool.aux[idx];
+                    medium = (int)f2u(x.w);
+                    if (medium >= 0) {
+                        slot = (int)idx;
+                        V4 ro = a.pool.ray_o[idx], rd = a.pool.ray_d[idx], h = a.pool.hit[idx];
+                        o = xyz(ro); d = xyz(rd);
+                        t_hit = (int)f2u(h.w) == kNoHit ? LJ_INF : h.x;
+                        rng.state = (uint64_t)f2u(m.z) | ((uint64_t)f2u(m.w) << 32);
+                        rng.inc = pcg_inc(path_stream((uint64_t)f2u(m.x) * a.rp.spp_total + f2u(x.z)));
+                        tr = mk3(1); pd = mk3(1); pn = mk3(1);
+                        if (track_begin(sc.media[medium], o, d, rd.w, rng, ts)) busy = true;
+                        else a.pool.meta[idx] = mk4(m.x, m.y, u2f((uint32_t)rng.state), u2f((uint32_t)(rng.state >> 32)));  // channel draw only
+                    }
+                }
+            }
+        }
+        if (!__ballot_sync(0xffffffffu, busy)) {
+            if (drained) break;
+            continue;
+        }
+        for (bool first = true;; first = false) {
+            const unsigned bm = __ballot_sync(0xffffffffu, busy);
+            if (bm == 0) break;
+            if (!first && !drained && __popc(bm) < a.track_refill) break;
+            if (busy) {
+                int r = flight_step(sc.media[medium], o, d, t_hit, sc.options.max_null_collisions, rng, ts, tr, pd, pn);
+                if (r != kTrackContinue) {
+                    V4 t = a.pool.thr[slot], v0 = a.pool.vol0[slot], v1 = a.pool.vol1[slot], m = a.pool.meta[slot];
+                    float inv = 1 / avg3(pd);
+                    a.pool.thr[slot] = mk4(t.x * tr.x * inv, t.y * tr.y * inv, t.z * tr.z * inv, t.w);
+                    a.pool.vol0[slot] = mk4(v0.x * pd.x, v0.y * pd.y, v0.z * pd.z, v0.w);
+                    a.pool.vol1[slot] = mk4(v1.x * pn.x, v1.y * pn.y, v1.z * pn.z, v1.w);
+                    a.pool.meta[slot] = mk4(m.x, m.y, u2f((uint32_t)rng.state), u2f((uint32_t)(rng.state >> 32)));
+                    if (r == kTrackScatter) a.pool.hit[slot] = mk4(ts.accum_t, 0, 0, u2f((uint32_t)kScatter));
+                    busy = false;
+                }
+            }
+        }
+    }
 }
 
 // K4 + K5 for the volpath integrator (lj_volpath.h)
@@ -439,7 +572,7 @@ static int render_impl(lj_scene *s, const lj_render_opts *opts_in, float *d_out,
     if (d_var && !s->d_film_sq) LJ_CUDA(cudaMalloc(&s->d_film_sq, (size_t)npix * 16));
     if (!s->d_counters) LJ_CUDA(cudaMalloc(&s->d_counters, sizeof(unsigned long long) * C_TOTAL));
     if (!s->h_counters) LJ_CUDA(cudaMallocHost(&s->h_counters, sizeof(unsigned long long) * (C_TOTAL + 8)));
-    if (!s->d_cursors) LJ_CUDA(cudaMalloc(&s->d_cursors, 2 * sizeof(unsigned int)));
+    if (!s->d_cursors) LJ_CUDA(cudaMalloc(&s->d_cursors, 4 * sizeof(unsigned int)));
     unsigned long long *d_counters = s->d_counters;
     unsigned long long *h_counters = s->h_counters;  // C_COUNT final counters, then the ring of per-wave live-path counts
     unsigned long long *h_active = h_counters + C_TOTAL;
@@ -462,6 +595,8 @@ static int render_impl(lj_scene *s, const lj_render_opts *opts_in, float *d_out,
     a.refill_threshold = kRefillThreshold;
     if (const char *e = getenv("LJ_PRIM_MIN_LANES")) a.prim_min_lanes = atoi(e);
     if (const char *e = getenv("LJ_REFILL")) a.refill_threshold = atoi(e);
+    a.track_refill = 24;
+    if (const char *e = getenv("LJ_TRACK_REFILL")) a.track_refill = atoi(e);
     a.chunk = 64;
     if (const char *e = getenv("LJ_CHUNK")) a.chunk = std::max(32, atoi(e));
     int shade_occ = 4;  // resident CTAs per SM the shade kernel is compiled for (register cap), LJ_SHADE_OCC for tuning runs
@@ -469,7 +604,7 @@ static int render_impl(lj_scene *s, const lj_render_opts *opts_in, float *d_out,
 
     const int nb256 = (capacity + 255) / 256, nb128 = (capacity + 127) / 128;
     // persistent grid: exactly one wave of resident CTAs (SM count x the occupancy of k_trace)
-    static int trace_blocks = 0, walk_blocks = 1;
+    static int trace_blocks = 0, walk_blocks = 1, step_blocks = 1, flight_blocks = 1;
     if (trace_blocks == 0) {
 #if defined(LJ_HOSTSIM)
         trace_blocks = 1;
@@ -481,6 +616,11 @@ static int render_impl(lj_scene *s, const lj_render_opts *opts_in, float *d_out,
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a2, k_trace<2>, 128, 0);
         trace_blocks = std::max(1, sms) * std::max(1, std::min(a0, a1));
         walk_blocks = std::max(1, sms) * std::max(1, a2);
+        int a3 = 0, a4 = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a4, k_trace<3>, 128, 0);
+        step_blocks = std::max(1, sms) * std::max(1, a4);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a3, k_flight, 128, 0);
+        flight_blocks = std::max(1, sms) * std::max(1, a3);
 #endif
     }
     unsigned int *d_cursors = s->d_cursors;
@@ -518,10 +658,11 @@ static int render_impl(lj_scene *s, const lj_render_opts *opts_in, float *d_out,
             LJ_CUDA(cudaEventSynchronize(ev_copied[w % kRing]));
             if (h_active[w % kRing] == 0) { waves = w; marks.push_back(e0); marks.push_back(e1); marks.push_back(nullptr); break; }
         }
-        LJ_CUDA(cudaMemsetAsync(d_cursors, 0, 2 * sizeof(unsigned int), stream));
+        LJ_CUDA(cudaMemsetAsync(d_cursors, 0, 4 * sizeof(unsigned int), stream));
         LJ_LAUNCH(k_trace<0>, trace_blocks, 128, stream, sc, a);
         LJ_CUDA(cudaEventRecord(e2, stream));
         if (vol) {
+            if (sc.num_media > 0) { LJ_LAUNCH(k_flight, flight_blocks, 128, stream, sc, a); launches++; }
             LJ_LAUNCH(k_shade_vol, nb128, 128, stream, sc, a);
         } else switch (shade_occ) {
             case 5: LJ_LAUNCH(k_shade<5>, nb128, 128, stream, sc, a); break;
@@ -530,7 +671,8 @@ static int render_impl(lj_scene *s, const lj_render_opts *opts_in, float *d_out,
             default: LJ_LAUNCH(k_shade<4>, nb128, 128, stream, sc, a); break;
         }
         LJ_CUDA(cudaEventRecord(e3, stream));
-        if (vol) LJ_LAUNCH(k_trace<2>, walk_blocks, 128, stream, sc, a);
+        if (vol && s->has_grid_media) LJ_LAUNCH(k_trace<3>, step_blocks, 128, stream, sc, a);
+        else if (vol) LJ_LAUNCH(k_trace<2>, walk_blocks, 128, stream, sc, a);
         else LJ_LAUNCH(k_trace<1>, trace_blocks, 128, stream, sc, a);
         LJ_CUDA(cudaEventRecord(e4, stream));
         launches += 3;
