@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 #define LJ_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
 #define LJ_LANE() ((int)(threadIdx.x & 31))
+#define LJ_WARP_WIDTH 32
 #define LJ_GRID_CONSTANT __grid_constant__
 __device__ __forceinline__ float lj_warp_min(float x) {
     for (int o = 16; o > 0; o >>= 1) x = fminf(x, __shfl_xor_sync(0xffffffffu, x, o));

@@ -33,6 +33,8 @@ struct PathPool {
     V4 *sh_o;   // walk origin.xyz, bits((medium + 1) & 0xffff | budget << 16)
     V4 *sh_pl;  // light point.xyz, bits(walk rng seed)
                 // (volpath reuses sh_d.w as pdf_dir = pdf_scatter * G, < 0: no walk; sh_c.w as pdf_nee)
+    // one bit per slot, one word per warp of the shade kernel: the slot carries an NEE shadow ray / walk this wave
+    uint32_t *sh_mask;
     int capacity;
 };
 

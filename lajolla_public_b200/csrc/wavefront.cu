@@ -38,8 +38,9 @@ struct WaveArgs {
     unsigned long long total_items;  // padded pixels * samples in this call
     int tiles_x, tiles_y;
     int prim_min_lanes, refill_threshold;  // scheduling policy of k_trace
-    int chunk;                             // slots a warp takes from the cursor at a time
+    int chunk, shadow_chunk;               // slots a warp takes from the cursor at a time
     int track_refill;                      // k_flight / walk: refill once fewer lanes than this are tracking
+    int trav_every;                        // k_trace<3>: traversal phase at least every this many passes
 };
 
 __device__ __forceinline__ void warp_add(unsigned long long *ctr, unsigned v) {
@@ -150,17 +151,20 @@ __global__ void __launch_bounds__(256) k_regen(const LJ_GRID_CONSTANT DevScene s
 // they are postponed (pushed as a group) so the tests run with more of the warp active.
 // SHADOW = false: closest hit of pool.ray -> pool.hit.  SHADOW = true: any hit of the NEE segment; an
 // unoccluded segment adds its contribution to pool.rad.
+#ifndef LJ_SHADOW_MIN_BLOCKS
+#define LJ_SHADOW_MIN_BLOCKS 8
+#endif
 #ifndef LJ_WALK_MIN_BLOCKS
 #define LJ_WALK_MIN_BLOCKS 5
 #endif
-constexpr int kRefillThreshold = 20;  // defaults; LJ_REFILL / LJ_PRIM_MIN_LANES override them for tuning runs
-constexpr int kPrimMinLanes = 12;
+constexpr int kRefillThreshold = 24;  // defaults; LJ_REFILL / LJ_PRIM_MIN_LANES override them for tuning runs
+constexpr int kPrimMinLanes = 10;
 
 // MODE 2 (volpath NEE walk, homework2.tex:459-510): the lane keeps its slot across the segments of one walk --
 // each segment is a closest-hit traversal, followed by ratio tracking over it and the index-matched / opaque test
 // (nee_walk_step); the walk's transmittance products stay in registers until the segment chain ends.
 template <int MODE>
-__global__ void __launch_bounds__(128, MODE >= 2 ? LJ_WALK_MIN_BLOCKS : 1) k_trace(const LJ_GRID_CONSTANT DevScene sc, const LJ_GRID_CONSTANT WaveArgs a) {
+__global__ void __launch_bounds__(128, MODE >= 2 ? LJ_WALK_MIN_BLOCKS : (MODE == 1 ? LJ_SHADOW_MIN_BLOCKS : 8)) k_trace(const LJ_GRID_CONSTANT DevScene sc, const LJ_GRID_CONSTANT WaveArgs a) {
     constexpr bool SHADOW = MODE == 1;
     constexpr bool WALK = MODE >= 2;   // 2: whole ratio-tracking loop when a segment ends (homogeneous media: 1-2 collisions)
     constexpr bool STEP = MODE == 3;   // 3: ratio tracking one collision per pass (heterogeneous media: ~100 per segment)
@@ -168,6 +172,7 @@ __global__ void __launch_bounds__(128, MODE >= 2 ? LJ_WALK_MIN_BLOCKS : 1) k_tra
     TrackState ts;
     float seg_tfar = 0, next_t = 0;
     bool tracking = false;  // WALK: the lane is ratio tracking over the segment it just traversed
+    unsigned pass = 0;
     const unsigned n = (unsigned)a.pool.capacity;
     unsigned int *cursor = &a.cursors[MODE == 0 ? 0 : 1];
     const int lane = LJ_LANE();
@@ -178,70 +183,94 @@ __global__ void __launch_bounds__(128, MODE >= 2 ? LJ_WALK_MIN_BLOCKS : 1) k_tra
     bool drained = false;  // warp-uniform: the cursor ran past the pool and the warp's own run is used up
     bool global_out = false;
     unsigned chunk_next = 0, chunk_end = 0;
-    const unsigned chunk = (unsigned)a.chunk;
+    unsigned cur_mask = 0, cur_word = 0;  // MODE >= 1: unread bits of the warp's current sh_mask word
+    const unsigned chunk = (unsigned)(MODE == 1 ? a.shadow_chunk : a.chunk);  // walks: small runs, their cost per slot varies a lot
     unsigned traced = 0, node_steps = 0, prim_tests = 0;
     for (;;) {
         // ---- fetch: lanes without a ray take the next slots.  The warp owns a private run of slots [chunk_next,
         // chunk_end) and goes to the global cursor only when that runs out: one same-address atomic per a.chunk
         // slots instead of one per refill.
-        unsigned want = drained ? 0u : __ballot_sync(0xffffffffu, !has_ray);
-        if (want) {
-            const unsigned cnt = (unsigned)__popc(want);
-            const unsigned lim = chunk_end < n ? chunk_end : n;
-            const unsigned left = chunk_next < lim ? lim - chunk_next : 0u;
-            unsigned nb = 0;
-            bool fresh = false;
-            if (cnt > left && !global_out) {
-                if (lane == 0) nb = atomicAdd(cursor, chunk);
-                nb = __shfl_sync(0xffffffffu, nb, 0);
-                if (nb >= n) global_out = true; else fresh = true;
-            }
-            const unsigned rank = (unsigned)__popc(want & ((1u << lane) - 1));
-            const unsigned idx = rank < left ? chunk_next + rank : (fresh ? nb + (rank - left) : 0xffffffffu);
-            if (fresh) { chunk_next = nb + (cnt - left); chunk_end = nb + chunk; }
-            else chunk_next += cnt < left ? cnt : left;
-            drained = global_out && chunk_next >= (chunk_end < n ? chunk_end : n);
-            if (!has_ray) {
-                if (idx < n) {
-                    slot = (int)idx;
-                    if (WALK) {
-                        V4 sd = a.pool.sh_d[slot];
-                        if (sd.w >= 0) {
-                            V4 so = a.pool.sh_o[slot], pl = a.pool.sh_pl[slot], cc = a.pool.sh_c[slot];
-                            uint32_t mb = f2u(so.w);
-                            wk.pc = xyz(so); wk.dir = xyz(sd); wk.pl = xyz(pl);
-                            wk.T_light = mk3(1); wk.p_nee = mk3(1); wk.p_dir = mk3(1);
-                            wk.c = xyz(cc); wk.pdf_nee = cc.w; wk.pdf_dir = sd.w;
-                            wk.medium = (int)(mb & 0xffffu) - 1;
-                            wk.budget = mb >> 16;
-                            wk.shadow_bounces = 0;
-                            wk.rng = pcg_init(((uint64_t)(unsigned)slot << 32) | f2u(pl.w), a.rp.seed);
-                            float tn;
-                            nee_walk_segment(sc, wk, tn, seg_tfar);
-                            trav_init(tr, wk.pc, wk.dir, tn, seg_tfar);
-                            a.pool.sh_d[slot] = mk4(sd.x, sd.y, sd.z, -1.f);
-                            has_ray = true;
-                        }
-                    } else if (SHADOW) {
-                        V4 sd = a.pool.sh_d[slot];
-                        if (sd.w >= 0) {
-                            // The segment starts at the shaded vertex: pool.ray_o if the path continued (the
-                            // extension ray starts there too); if it ended, ray_o still holds the previous
-                            // origin and the vertex is rebuilt from the old ray and its hit distance.
-                            V4 o = a.pool.ray_o[slot];
-                            V3 org = xyz(o);
-                            if (!(f2u(a.pool.meta[slot].y) & kAlive)) org = org + xyz(a.pool.ray_d[slot]) * a.pool.hit[slot].x;
-                            trav_init(tr, org, xyz(sd), sc.shadow_eps, sd.w);
-                            a.pool.sh_d[slot] = mk4(sd.x, sd.y, sd.z, -1.f);
-                            has_ray = true;
-                        }
-                    } else if (f2u(a.pool.meta[slot].y) & kAlive) {
-                        V4 o = a.pool.ray_o[slot], d = a.pool.ray_d[slot];
-                        trav_init(tr, xyz(o), xyz(d), o.w, d.w);
-                        has_ray = true;
-                    }
-                    traced += has_ray ? 1u : 0u;
+        if (MODE == 0) {
+            unsigned want = drained ? 0u : __ballot_sync(0xffffffffu, !has_ray);
+            if (want) {
+                const unsigned cnt = (unsigned)__popc(want);
+                const unsigned lim = chunk_end < n ? chunk_end : n;
+                const unsigned left = chunk_next < lim ? lim - chunk_next : 0u;
+                unsigned nb = 0;
+                bool fresh = false;
+                if (cnt > left && !global_out) {
+                    if (lane == 0) nb = atomicAdd(cursor, chunk);
+                    nb = __shfl_sync(0xffffffffu, nb, 0);
+                    if (nb >= n) global_out = true; else fresh = true;
                 }
+                const unsigned rank = (unsigned)__popc(want & ((1u << lane) - 1));
+                const unsigned idx = rank < left ? chunk_next + rank : (fresh ? nb + (rank - left) : 0xffffffffu);
+                if (fresh) { chunk_next = nb + (cnt - left); chunk_end = nb + chunk; }
+                else chunk_next += cnt < left ? cnt : left;
+                drained = global_out && chunk_next >= (chunk_end < n ? chunk_end : n);
+                if (!has_ray && idx < n && (f2u(a.pool.meta[idx].y) & kAlive)) {
+                    slot = (int)idx;
+                    V4 o = a.pool.ray_o[slot], d = a.pool.ray_d[slot];
+                    trav_init(tr, xyz(o), xyz(d), o.w, d.w);
+                    has_ray = true;
+                    traced++;
+                }
+            }
+        } else {
+            // Shadow rays / walks exist for a fraction of the slots only: the shade kernel left one bit per slot in
+            // pool.sh_mask, and lanes are handed the set bits of the warp's current word (chunk_next counts WORDS here),
+            // so no lane ever loads the record of a slot without a ray.
+            while (!drained) {
+                const unsigned want = __ballot_sync(0xffffffffu, !has_ray);
+                if (!want) break;
+                if (cur_mask == 0) {
+                    if (chunk_next >= chunk_end) {
+                        unsigned nb = 0;
+                        if (lane == 0) nb = atomicAdd(cursor, chunk);
+                        nb = __shfl_sync(0xffffffffu, nb, 0);
+                        if (nb >= n) { drained = true; break; }
+                        chunk_next = nb / LJ_WARP_WIDTH;
+                        chunk_end = ((nb + chunk < n ? nb + chunk : n) + LJ_WARP_WIDTH - 1) / LJ_WARP_WIDTH;
+                    }
+                    cur_word = chunk_next++;
+                    cur_mask = a.pool.sh_mask[cur_word];
+                    continue;
+                }
+                const unsigned cnt = (unsigned)__popc(want), avail = (unsigned)__popc(cur_mask);
+                const unsigned take = cnt < avail ? cnt : avail;
+                const unsigned rank = (unsigned)__popc(want & ((1u << lane) - 1));
+                if (!has_ray && rank < take) {
+                    slot = (int)(cur_word * LJ_WARP_WIDTH + __fns(cur_mask, 0, (int)rank + 1));
+                    V4 sd = a.pool.sh_d[slot];
+                    if (WALK) {
+                        V4 so = a.pool.sh_o[slot], pl = a.pool.sh_pl[slot], cc = a.pool.sh_c[slot];
+                        uint32_t mb = f2u(so.w);
+                        wk.pc = xyz(so); wk.dir = xyz(sd); wk.pl = xyz(pl);
+                        wk.T_light = mk3(1); wk.p_nee = mk3(1); wk.p_dir = mk3(1);
+                        wk.c = xyz(cc); wk.pdf_nee = cc.w; wk.pdf_dir = sd.w;
+                        wk.medium = (int)(mb & 0xffffu) - 1;
+                        wk.budget = mb >> 16;
+                        wk.shadow_bounces = 0;
+                        wk.rng = pcg_init(((uint64_t)(unsigned)slot << 32) | f2u(pl.w), a.rp.seed);
+                        float tn;
+                        nee_walk_segment(sc, wk, tn, seg_tfar);
+                        trav_init(tr, wk.pc, wk.dir, tn, seg_tfar);
+                        tracking = false;
+                    } else {
+                        // The segment starts at the shaded vertex: pool.ray_o if the path continued (the
+                        // extension ray starts there too); if it ended, ray_o still holds the previous
+                        // origin and the vertex is rebuilt from the old ray and its hit distance.
+                        V4 o = a.pool.ray_o[slot];
+                        V3 org = xyz(o);
+                        if (!(f2u(a.pool.meta[slot].y) & kAlive)) org = org + xyz(a.pool.ray_d[slot]) * a.pool.hit[slot].x;
+                        trav_init(tr, org, xyz(sd), sc.shadow_eps, sd.w);
+                    }
+                    has_ray = true;
+                    traced++;
+                }
+                const unsigned last = __fns(cur_mask, 0, (int)take);  // position of the last bit handed out
+                cur_mask &= ~((2u << last) - 1u);
+                if (take == cnt) break;
             }
         }
         if (!__ballot_sync(0xffffffffu, has_ray)) {
@@ -261,7 +290,9 @@ __global__ void __launch_bounds__(128, MODE >= 2 ? LJ_WALK_MIN_BLOCKS : 1) k_tra
             // (segment end -> tracking step -> surface test -> next segment).
             const unsigned km = STEP ? __ballot_sync(0xffffffffu, tracking || (has_ray && !work)) : 0u;
             const unsigned busy = wm | km;
-            const bool trav_phase = !STEP || __popc(wm) >= __popc(km);
+            // (traversal also gets every trav_every-th pass, so a few lanes with short segments left to traverse do not
+            //  sit out a whole ~100-collision tracking run of the others)
+            const bool trav_phase = !STEP || __popc(wm) >= __popc(km) || (wm != 0 && (++pass % (unsigned)a.trav_every) == 0);
             if (busy == 0) break;
             // refill once too few lanes are still busy (never before the pass after a fetch made progress)
             if (!first && !drained && __popc(busy) < (STEP ? a.track_refill : a.refill_threshold)) break;
@@ -362,6 +393,7 @@ template <int MIN_BLOCKS>
 __global__ void __launch_bounds__(128, MIN_BLOCKS) k_shade(const LJ_GRID_CONSTANT DevScene sc, const LJ_GRID_CONSTANT WaveArgs a) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     ShadeCounters cnt = {0, 0, 0, 0};
+    bool has_shadow = false;
     if (i < a.pool.capacity) {
         uint32_t flags = f2u(a.pool.meta[i].y);
         if (flags & kAlive) {
@@ -381,7 +413,12 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_shade(const LJ_GRID_CONSTAN
                         (s.flags & kAlive) != 0);
 #endif
             store_state(a.pool, i, s, (s.flags & kAlive) != 0);
+            has_shadow = s.sh_tfar >= 0;
         }
+    }
+    {   // capacity is a multiple of the block size: whole warps are in range
+        unsigned m = __ballot_sync(0xffffffffu, has_shadow);
+        if (LJ_LANE() == 0 && i < a.pool.capacity) a.pool.sh_mask[i / LJ_WARP_WIDTH] = m;
     }
     warp_add(&a.counters[C_BOUNCES_STRIPED + ((blockIdx.x * 4 + (threadIdx.x >> 5)) & (kStripes - 1))], cnt.bounces);
 }
@@ -471,6 +508,7 @@ __global__ void __launch_bounds__(128) k_flight(const LJ_GRID_CONSTANT DevScene 
 __global__ void __launch_bounds__(128) k_shade_vol(const LJ_GRID_CONSTANT DevScene sc, const LJ_GRID_CONSTANT WaveArgs a) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     ShadeCounters cnt = {0, 0, 0, 0};
+    bool has_shadow = false;
     if (i < a.pool.capacity) {
         uint32_t flags = f2u(a.pool.meta[i].y);
         if (flags & kAlive) {
@@ -478,7 +516,12 @@ __global__ void __launch_bounds__(128) k_shade_vol(const LJ_GRID_CONSTANT DevSce
             load_state_vol(a.pool, i, s);
             shade_vol_path(sc, a.rp, s, cnt);
             store_state_vol(a.pool, i, s, (s.flags & kAlive) != 0);
+            has_shadow = s.sh_pdf_dir >= 0;
         }
+    }
+    {
+        unsigned m = __ballot_sync(0xffffffffu, has_shadow);
+        if (LJ_LANE() == 0 && i < a.pool.capacity) a.pool.sh_mask[i / LJ_WARP_WIDTH] = m;
     }
     warp_add(&a.counters[C_BOUNCES_STRIPED + ((blockIdx.x * 4 + (threadIdx.x >> 5)) & (kStripes - 1))], cnt.bounces);
 }
@@ -515,7 +558,7 @@ static int ensure_pool(lj_scene *s, int capacity, bool vol) {
     if (s->pool_capacity == capacity && s->pool_block && (s->pool.vol0 != nullptr) == vol) return LJ_OK;
     if (s->pool_block) { cudaFree(s->pool_block); s->pool_block = nullptr; }
     const int kFields = vol ? 14 : 9;
-    LJ_CUDA(cudaMalloc(&s->pool_block, (size_t)capacity * sizeof(V4) * kFields));
+    LJ_CUDA(cudaMalloc(&s->pool_block, (size_t)capacity * sizeof(V4) * kFields + (size_t)capacity / LJ_WARP_WIDTH * sizeof(uint32_t)));
     V4 *base = (V4 *)s->pool_block;
     PathPool &p = s->pool;
     p.ray_o = base + (size_t)capacity * 0; p.ray_d = base + (size_t)capacity * 1; p.hit = base + (size_t)capacity * 2;
@@ -526,6 +569,7 @@ static int ensure_pool(lj_scene *s, int capacity, bool vol) {
         p.vol0 = base + (size_t)capacity * 9; p.vol1 = base + (size_t)capacity * 10; p.vol2 = base + (size_t)capacity * 11;
         p.sh_o = base + (size_t)capacity * 12; p.sh_pl = base + (size_t)capacity * 13;
     }
+    p.sh_mask = (uint32_t *)(base + (size_t)capacity * kFields);
     p.capacity = capacity;
     s->pool_capacity = capacity;
     return LJ_OK;
@@ -597,6 +641,10 @@ static int render_impl(lj_scene *s, const lj_render_opts *opts_in, float *d_out,
     if (const char *e = getenv("LJ_REFILL")) a.refill_threshold = atoi(e);
     a.track_refill = 24;
     if (const char *e = getenv("LJ_TRACK_REFILL")) a.track_refill = atoi(e);
+    a.shadow_chunk = 128;
+    if (const char *e = getenv("LJ_SHADOW_CHUNK")) a.shadow_chunk = std::max(32, atoi(e));
+    a.trav_every = 4;
+    if (const char *e = getenv("LJ_TRAV_EVERY")) a.trav_every = std::max(1, atoi(e));
     a.chunk = 64;
     if (const char *e = getenv("LJ_CHUNK")) a.chunk = std::max(32, atoi(e));
     int shade_occ = 4;  // resident CTAs per SM the shade kernel is compiled for (register cap), LJ_SHADE_OCC for tuning runs

@@ -19,6 +19,7 @@
 #define __restrict__
 #define LJ_GRID_CONSTANT
 #define LJ_LANE() 0
+#define LJ_WARP_WIDTH 1
 
 struct SimDim3 { unsigned x = 1, y = 1, z = 1; };
 inline thread_local SimDim3 threadIdx, blockIdx, blockDim, gridDim;
@@ -85,4 +86,9 @@ inline float lj_warp_max(float x) { return x; }
 inline double lj_warp_sum(double x) { return x; }
 inline int lj_float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
 inline unsigned __activemask() { return 1u; }
+// position of the offset-th set bit of mask at or above base (offset >= 1), 0xffffffff if there is none
+inline unsigned __fns(unsigned mask, unsigned base, int offset) {
+    for (unsigned b = base; b < 32; b++) if ((mask >> b) & 1u) { if (--offset == 0) return b; }
+    return 0xffffffffu;
+}
 inline bool __any_sync(unsigned, bool p) { return p; }
