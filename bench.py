@@ -41,6 +41,16 @@ VOLPATH = {"volpath_test6", "hetvol", "hetvol_colored", "vol_cbox_teapot"}
 BYTES_PER_EXTENSION_RAY = 104  # 2R + 2H, R = 32 B ray, H = 20 B hit
 
 
+def workload_name(key, w, h, full_spp):
+    """The same string in both arms (b200 and --impl reference)."""
+    return f"{key} {w}x{h} {'volpath' if key in VOLPATH else 'path'} integrator, {full_spp} spp"
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_trace<0> launch (3.9 M rays) from the ncu --set full capture
+# profiles/r01n_sponza_ncu.txt (sponza, steady-state wave); other workloads have no capture of that kernel
+NCU_TRAFFIC_BYTES_PER_LAUNCH = {"sponza": 213.118720e6 + 57.262592e6}
+
+
 def load_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -140,7 +150,7 @@ def run_reference(args):
         "impl": "reference", "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(secs), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{key} {w}x{h} {'volpath' if key in VOLPATH else 'path'} integrator, {full_spp} spp (timed on a {spp} spp sample)"},
+        "config": {"workload": workload_name(key, w, h, full_spp), "timed_sample_spp": spp},
         "mrays_per_s": mrays,
         "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -268,7 +278,7 @@ def main():
             "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{key} {w}x{h} {'volpath' if key in VOLPATH else 'path'} integrator, {spp} spp per GPU ({total_spp} spp image)",
+            "config": {"workload": workload_name(key, w, h, full_spp), "spp_per_gpu": spp, "image_spp": total_spp,
                        "l2_policy": f"path pool (4M slots x {224 if key in VOLPATH else 144} B) streams through HBM every wave, larger than the 126 MB L2",
                        "scene_source": "reference scene flattened to .ljs", "parallelism": f"spp-split x{world} + NCCL reduce"},
             "mrays_per_s": (agg["closest"] + agg["shadow"]) * world / (ms_total / 1e3) / 1e6,
@@ -281,8 +291,9 @@ def main():
             "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": int(cdesc_bytes),
                     "d2h_bytes_per_step": int(npix * 3 * 4), "includes": "lj_scene_create (upload + GPU BVH/mip build) + lj_render + D2H", "parts": e2e_parts},
             "gpu_launches": int(agg["launches"]),
-            "roofline": {"bound": "hbm", "kernel": "k_extend", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
+            "roofline": {"bound": "hbm", "kernel": "k_trace<0> (closest-hit extension)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH.get(key) if spp == full_spp else None,
+                         "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r01n_sponza_ncu.txt)", "peak_kind": peak_kind,
                          "algorithmic_bytes_per_ray": BYTES_PER_EXTENSION_RAY,
                          "rays_per_launch": agg["closest"] / max(agg["extend_launches"], 1),
                          "avg_launch_ms": agg["extend_ms"] / max(agg["extend_launches"], 1)},
