@@ -269,6 +269,21 @@ def main():
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = npix * spp * world * e2e_steps / float(e2e_s.item()) / 1e6
 
+    # L2-side bound: BVH nodes and primitives are L2-resident; measured L2 copy bandwidth of this GPU
+    # (two 24 MB buffers, both inside the 126 MB L2) against the bytes the traversal kernels fetch, counted live.
+    l2_peak = None
+    if rank == 0:
+        xa = torch.empty(6 << 20, dtype=torch.float32, device="cuda"); xb = torch.empty_like(xa)
+        for _ in range(5):
+            xb.copy_(xa)
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0.record(stream)
+        for _ in range(50):
+            xb.copy_(xa)
+        l1.record(stream)
+        torch.cuda.synchronize()
+        l2_peak = 2 * xa.numel() * 4 * 50 / (l0.elapsed_time(l1) / 1e3) / 1e9
+        del xa, xb
     if rank == 0:
         peak, peak_kind = load_peaks()
         value = npix * spp * world * args.steps / (ms_total / 1e3) / 1e6
@@ -297,6 +312,11 @@ def main():
                          "algorithmic_bytes_per_ray": BYTES_PER_EXTENSION_RAY,
                          "rays_per_launch": agg["closest"] / max(agg["extend_launches"], 1),
                          "avg_launch_ms": agg["extend_ms"] / max(agg["extend_launches"], 1)},
+            "roofline_l2": {"bound": "l2", "kernel": "k_trace<0> + k_trace<1|2|3>", "unit": "GB/s", "peak": l2_peak,
+                            "peak_kind": "measured here: torch copy of 24 MB <-> 24 MB, L2-resident",
+                            "achieved": (agg["node_steps"] * 80 + agg["prim_tests"] * 48) / max((agg["extend_ms"] + agg["shadow_ms"]) / 1e3, 1e-9) / 1e9,
+                            "frac": (agg["node_steps"] * 80 + agg["prim_tests"] * 48) / max((agg["extend_ms"] + agg["shadow_ms"]) / 1e3, 1e-9) / 1e9 / l2_peak,
+                            "bytes": "80 B per wide-node step + 48 B per primitive test, both counted by the kernels"},
             "bvh": {"prims": info.num_prims, "nodes": info.num_bvh_nodes, "width": info.bvh_width, "build_ms": info.bvh_build_ms,
                     "sah": info.sah_cost},
         }

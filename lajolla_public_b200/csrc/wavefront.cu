@@ -554,6 +554,42 @@ __global__ void k_resolve(const float *film, const float *film_sq, int npix, flo
     }
 }
 
+// The five auxiliary integrators of render.cpp:12-69 (depth, shadingNormal, meanCurvature, rayDifferential,
+// mipmapLevel): one primary ray through each pixel centre, no sampling -- images are comparable pixel by pixel
+// with the reference's.
+__global__ void __launch_bounds__(128) k_aux(const LJ_GRID_CONSTANT DevScene sc, int integrator, float *out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int w = sc.camera.width, h = sc.camera.height;
+    if (i >= w * h) return;
+    int x = i % w, y = i / w;
+    V3 o, d;
+    sample_primary(sc.camera, mk2((x + 0.5f) / w, (y + 0.5f) / h), o, d);
+    const float spread = init_ray_spread(w, h);
+    Hit hit;
+    V3 color = mk3(0);
+    if (trace8<false>(sc.nodes8, sc.prims, o, d, 0.f, LJ_INF, hit)) {
+        Vertex vx = make_vertex(sc, o, d, hit, 0.f, spread);
+        if (integrator == LJ_INT_DEPTH) {
+            color = mk3(distance(vx.position, o));
+        } else if (integrator == LJ_INT_SHADING_NORMAL) {
+            color = vx.shading_frame.n;
+        } else if (integrator == LJ_INT_MEAN_CURVATURE) {
+            color = mk3(vx.mean_curvature);
+        } else if (integrator == LJ_INT_RAY_DIFFERENTIAL) {
+            color = mk3(0.f, spread, 0.f);
+        } else if (vx.material_id >= 0) {  // LJ_INT_MIPMAP_LEVEL: the texture get_texture() names (material.cpp:68-88)
+            const DevMaterial &m = sc.materials[vx.material_id];
+            const DevTexture &t = m.tex[m.type == LJ_MAT_ROUGHDIELECTRIC ? 1 : 0];
+            if (t.kind == LJ_TEX_IMAGE && m.type != LJ_MAT_DISNEY_CLEARCOAT) {
+                const DevImage &im = sc.images3[t.image_id];
+                float scaled = (float)(im.w[0] > im.h[0] ? im.w[0] : im.h[0]) * fmaxf(t.uscale, t.vscale) * vx.uv_screen_size;
+                color = mk3(log2f(fmaxf(scaled, 1e-8f)));
+            }
+        }
+    }
+    out[3 * i] = color.x; out[3 * i + 1] = color.y; out[3 * i + 2] = color.z;
+}
+
 static int ensure_pool(lj_scene *s, int capacity, bool vol) {
     if (s->pool_capacity == capacity && s->pool_block && (s->pool.vol0 != nullptr) == vol) return LJ_OK;
     if (s->pool_block) { cudaFree(s->pool_block); s->pool_block = nullptr; }
@@ -590,8 +626,16 @@ static int render_impl(lj_scene *s, const lj_render_opts *opts_in, float *d_out,
     memset(&opts, 0, sizeof(opts));
     if (opts_in) opts = *opts_in;
     const DevScene &sc = s->dev;
+    if (sc.options.integrator >= LJ_INT_DEPTH && sc.options.integrator <= LJ_INT_MIPMAP_LEVEL) {  // render.cpp:157-163
+        int npx = sc.camera.width * sc.camera.height;
+        LJ_LAUNCH(k_aux, (npx + 127) / 128, 128, stream, sc, sc.options.integrator, d_out);
+        LJ_CUDA(cudaStreamSynchronize(stream));
+        LJ_CUDA(cudaGetLastError());
+        if (stats) { memset(stats, 0, sizeof(*stats)); stats->kernel_launches = 1; stats->closest_rays = (uint64_t)npx; }
+        return LJ_OK;
+    }
     if (sc.options.integrator != LJ_INT_PATH && sc.options.integrator != LJ_INT_VOLPATH) {
-        set_error("integrator not supported by the device path (path and volpath are)");
+        set_error("unknown integrator");
         return LJ_ERR_UNSUPPORTED;
     }
     const bool vol = sc.options.integrator == LJ_INT_VOLPATH;

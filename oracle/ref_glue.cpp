@@ -193,6 +193,7 @@ void ljo_scene_free(void *h) { delete (Scene *)h; }
 // Joins the reference's worker threads (parallel.cpp:258-274); without it the process hangs at exit.
 void ljo_shutdown(void) { if (g_parallel) { parallel_cleanup(); g_parallel = false; } }
 
+void ljo_set_integrator(void *h, int integrator) { ((Scene *)h)->options.integrator = (Integrator)integrator; }  // scene.h:14-22
 void ljo_set_spp(void *h, int spp) { ((Scene *)h)->options.samples_per_pixel = spp; }
 
 // Flatten to the .ljs container (layout documented in lajolla_public_b200/ljs.py).

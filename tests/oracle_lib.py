@@ -31,6 +31,7 @@ def lib():
         l.ljo_scene_load.argtypes = [C.c_char_p, C.c_int]
         l.ljo_scene_free.argtypes = [C.c_void_p]
         l.ljo_set_spp.argtypes = [C.c_void_p, C.c_int]
+        l.ljo_set_integrator.argtypes = [C.c_void_p, C.c_int]
         l.ljo_scene_dump.argtypes = [C.c_void_p, C.c_char_p]
         l.ljo_scene_info.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]
         l.ljo_light_table.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
@@ -78,6 +79,9 @@ class RefScene:
         os.makedirs(os.path.dirname(out_path), exist_ok=True)
         if lib().ljo_scene_dump(self.h, os.fsencode(out_path)) != 0:
             raise RuntimeError("dump failed")
+
+    def set_integrator(self, integrator):
+        lib().ljo_set_integrator(self.h, integrator)
 
     def set_spp(self, spp):
         lib().ljo_set_spp(self.h, spp)

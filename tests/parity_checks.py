@@ -306,3 +306,53 @@ def check_medium_parity(scene, ref, n=20000, seed=6):
         assert rel_err(a["phase_pdf"], b["phase_pdf"]).max() < 1e-4
         out[mid] = dict(inside=float((np.abs(b["sigma_s"]).max(axis=1) > 0).mean()))
     return out
+
+
+AUX_INTEGRATORS = {"depth": 0, "shading_normal": 1, "mean_curvature": 2, "ray_differential": 3, "mipmap_level": 4}
+
+
+def check_aux_parity(make_scene, ref, desc):
+    """The auxiliary integrators (render.cpp:12-69) are deterministic -- one ray through each pixel centre -- so the
+    device image is compared with the reference's pixel by pixel.  `make_scene(desc)` builds the scene under test."""
+    import copy
+    out = {}
+    for name, code in AUX_INTEGRATORS.items():
+        d = copy.copy(desc)
+        d.options = copy.copy(desc.options)
+        d.options.integrator = code
+        sc = make_scene(d)
+        img = sc.render()
+        sc.close()
+        ref.set_integrator(code)
+        ref_img, _ = ref.render()
+        a, b = img.astype(np.float64), ref_img.astype(np.float64)
+        hit_a, hit_b = np.abs(a).sum(axis=2) > 0, np.abs(b).sum(axis=2) > 0
+        if name == "depth":
+            assert (hit_a == hit_b).mean() > 0.9995   # silhouette pixels may fall on either side
+            both = hit_a & hit_b
+            e = np.abs(a - b)[both] / np.maximum(b[both], 1e-6)
+            assert np.quantile(e, 0.999) < 1e-4, np.quantile(e, [0.5, 0.999, 1])  # a pixel straddling an edge sees another surface
+            out[name] = float(np.median(e))
+        elif name == "shading_normal":
+            e = np.abs(a - b).max(axis=2)
+            assert np.median(e) < 1e-5 and np.quantile(e, 0.995) < 2e-3, np.quantile(e, [0.5, 0.995, 1])
+            out[name] = float(np.median(e))
+        elif name == "mean_curvature":
+            fa, fb = np.isfinite(a), np.isfinite(b)
+            assert (fa == fb).mean() > 0.98
+            ok = fa & fb & (np.abs(b) < 1e3)
+            e = np.abs(a - b)[ok] / np.maximum(np.abs(b[ok]), 1e-3)
+            assert np.median(e) < 1e-4 and np.quantile(e, 0.99) < 5e-2, np.quantile(e, [0.5, 0.99])
+            out[name] = float(np.median(e))
+        elif name == "ray_differential":
+            assert np.abs(a - b).max() < 1e-9 + 1e-6 * np.abs(b).max()
+            out[name] = 0.0
+        else:  # mip level = log2(footprint): absolute
+            both = hit_a & hit_b
+            assert (hit_a == hit_b).mean() > 0.995
+            e = np.abs(a - b)[both]
+            if e.size:
+                assert np.median(e) < 1e-4 and np.quantile(e, 0.99) < 5e-2, np.quantile(e, [0.5, 0.99, 1])
+                out[name] = float(np.median(e))
+    ref.set_integrator(desc.options.integrator)
+    return out

@@ -206,6 +206,16 @@ def test_render_against_golden_tiles(oracle):
     assert np.median(np.abs(lum_t[lit] - lum_g[lit]) / lum_g[lit]) < 0.03
 
 
+@pytest.mark.parametrize("name", ["cbox", "veach_mi", "sponza"])
+def test_aux_integrators_pixel_exact(oracle, name):
+    """The deterministic debug integrators (render.cpp:12-69): device image == reference image, pixel by pixel
+    (depth 1e-4 relative, shading normals 1e-5 median, mean curvature, mip level)."""
+    from lajolla_public_b200 import ljs
+    desc = ljs.load(oracle.scene_ljs(name))
+    ref = oracle.RefScene(oracle.scene_xml(name))
+    record("aux_parity", dict(scene=name, **pc.check_aux_parity(lambda d: lj.Scene(d), ref, desc)))
+
+
 def test_sample_range_split_is_additive(oracle):
     """Multi-GPU partition property: spp blocks rendered separately sum to the single render."""
     sc, _ = pair(oracle, "cbox")

@@ -129,3 +129,16 @@ def test_volpath_matches_oracle_mean(oracle, name, spp, ref_spp):
     ref_img, _ = ref.render(spp=ref_spp)
     assert np.all(np.isfinite(img))
     assert np.allclose(img.mean(axis=(0, 1)), ref_img.mean(axis=(0, 1)), rtol=0.03), (img.mean(axis=(0, 1)), ref_img.mean(axis=(0, 1)))
+
+
+def test_aux_integrators_pixel_exact(oracle):
+    """depth / shadingNormal / meanCurvature / rayDifferential / mipmapLevel of veach_mi (spheres + meshes)."""
+    from lajolla_public_b200 import ljs
+    desc = ljs.load(oracle.scene_ljs("veach_mi"))
+    ref = oracle.RefScene(oracle.scene_xml("veach_mi"), threads=4)
+
+    def make(d):
+        with hostsim_lib.simulated():
+            return lj.Scene(d)
+    with hostsim_lib.simulated():
+        pc.check_aux_parity(make, ref, desc)
