@@ -132,8 +132,8 @@ static cudaError_t exclusive_scan(void *tmp, size_t &tmp_bytes, const int *in, i
 
 cudaError_t build_bvh8(const DevScene &sc, const int *d_prim_shape, const int *d_prim_local, int n,
                        cudaStream_t stream, BvhResult *out) {
-    // search radius of the PLOC neighbour search: LJ_PLOC_RADIUS in [1, 64] (default 16)
-    int radius = 16;
+    // search radius of the PLOC neighbour search: LJ_PLOC_RADIUS in [1, 64] (default 32)
+    int radius = 32;
     if (const char *e = getenv("LJ_PLOC_RADIUS")) radius = atoi(e);
     radius = radius < 1 ? 1 : (radius > 64 ? 64 : radius);
     cudaError_t err = cudaSuccess;

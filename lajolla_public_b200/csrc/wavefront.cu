@@ -40,7 +40,7 @@ struct WaveArgs {
     int prim_min_lanes, refill_threshold;  // scheduling policy of k_trace
     int chunk, shadow_chunk;               // slots a warp takes from the cursor at a time
     int track_refill;                      // k_flight / walk: refill once fewer lanes than this are tracking
-    int trav_every;                        // k_trace<3>: traversal phase at least every this many passes
+    int trav_min;                          // k_trace<3>: lanes that must wait to traverse before a traversal pass pre-empts tracking
 };
 
 __device__ __forceinline__ void warp_add(unsigned long long *ctr, unsigned v) {
@@ -172,7 +172,6 @@ __global__ void __launch_bounds__(128, MODE >= 2 ? LJ_WALK_MIN_BLOCKS : (MODE ==
     TrackState ts;
     float seg_tfar = 0, next_t = 0;
     bool tracking = false;  // WALK: the lane is ratio tracking over the segment it just traversed
-    unsigned pass = 0;
     const unsigned n = (unsigned)a.pool.capacity;
     unsigned int *cursor = &a.cursors[MODE == 0 ? 0 : 1];
     const int lane = LJ_LANE();
@@ -290,9 +289,9 @@ __global__ void __launch_bounds__(128, MODE >= 2 ? LJ_WALK_MIN_BLOCKS : (MODE ==
             // (segment end -> tracking step -> surface test -> next segment).
             const unsigned km = STEP ? __ballot_sync(0xffffffffu, tracking || (has_ray && !work)) : 0u;
             const unsigned busy = wm | km;
-            // (traversal also gets every trav_every-th pass, so a few lanes with short segments left to traverse do not
-            //  sit out a whole ~100-collision tracking run of the others)
-            const bool trav_phase = !STEP || __popc(wm) >= __popc(km) || (wm != 0 && (++pass % (unsigned)a.trav_every) == 0);
+            // (measured on hetvol: letting as few as 4 waiting lanes pre-empt the tracking phase is best -- segments are
+            //  short to traverse, and lanes that get through traversal quickly join the ~100-collision tracking runs)
+            const bool trav_phase = !STEP || km == 0 || __popc(wm) >= a.trav_min;
             if (busy == 0) break;
             // refill once too few lanes are still busy (never before the pass after a fetch made progress)
             if (!first && !drained && __popc(busy) < (STEP ? a.track_refill : a.refill_threshold)) break;
@@ -687,8 +686,8 @@ static int render_impl(lj_scene *s, const lj_render_opts *opts_in, float *d_out,
     if (const char *e = getenv("LJ_TRACK_REFILL")) a.track_refill = atoi(e);
     a.shadow_chunk = 128;
     if (const char *e = getenv("LJ_SHADOW_CHUNK")) a.shadow_chunk = std::max(32, atoi(e));
-    a.trav_every = 4;
-    if (const char *e = getenv("LJ_TRAV_EVERY")) a.trav_every = std::max(1, atoi(e));
+    a.trav_min = 4;
+    if (const char *e = getenv("LJ_TRAV_MIN")) a.trav_min = std::max(1, atoi(e));
     a.chunk = 64;
     if (const char *e = getenv("LJ_CHUNK")) a.chunk = std::max(32, atoi(e));
     int shade_occ = 4;  // resident CTAs per SM the shade kernel is compiled for (register cap), LJ_SHADE_OCC for tuning runs
