@@ -113,7 +113,7 @@ __global__ void k_sah(Tree2 tree, int root, double *out) {
 }
 
 template <typename T>
-cudaError_t dalloc(T **p, size_t n) { return cudaMalloc((void **)p, (n ? n : 1) * sizeof(T)); }
+cudaError_t dalloc(T **p, size_t n) { return lj_dev_alloc((void **)p, (n ? n : 1) * sizeof(T)); }
 
 }  // namespace
 
@@ -181,7 +181,7 @@ cudaError_t build_bvh8(const DevScene &sc, const int *d_prim_shape, const int *d
     }
 #else
     CK(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, keys, keys_sorted, vals, vals_sorted, n, 0, 63, stream));
-    CK(cudaMalloc(&cub_tmp, cub_bytes ? cub_bytes : 1));
+    CK(lj_dev_alloc(&cub_tmp, cub_bytes ? cub_bytes : 1));
     CK(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, keys, keys_sorted, vals, vals_sorted, n, 0, 63, stream));
 #endif
     LJ_LAUNCH(k_gather, nb, T, stream, vals_sorted, n, prims_unsorted, boxes, prims_sorted, tree, cluster_a);
@@ -191,7 +191,7 @@ cudaError_t build_bvh8(const DevScene &sc, const int *d_prim_shape, const int *d
     h_ints[0] = n; h_ints[1] = n;
     CK(cudaMemcpyAsync(d_ints, h_ints, 2 * sizeof(int), cudaMemcpyHostToDevice, stream));
     CK(exclusive_scan(nullptr, scan_bytes, nullptr, offset, n, stream));
-    CK(cudaMalloc(&scan_tmp, scan_bytes ? scan_bytes : 1));
+    CK(lj_dev_alloc(&scan_tmp, scan_bytes ? scan_bytes : 1));
     while (m > 1) {
         int g = (m + T - 1) / T;
         LJ_LAUNCH(k_ploc_nearest, g, T, stream, tree, cluster_a, m, radius, nearest);
@@ -255,13 +255,13 @@ cudaError_t build_bvh8(const DevScene &sc, const int *d_prim_shape, const int *d
     nodes = nullptr;
     prims = nullptr;
 done:
-    cudaFree(prims_unsorted); cudaFree(prims_sorted); cudaFree(prims); cudaFree(boxes);
-    cudaFree(tree.box); cudaFree(tree.left); cudaFree(tree.right); cudaFree(tree.count);
-    cudaFree(scene_bounds); cudaFree(cluster_a); cudaFree(cluster_b); cudaFree(cluster_tmp); cudaFree(nearest);
-    cudaFree(keep); cudaFree(offset); cudaFree(d_ints);
-    cudaFree(keys); cudaFree(keys_sorted); cudaFree(vals); cudaFree(vals_sorted);
-    cudaFree(queue_a); cudaFree(queue_b);
-    cudaFree(cub_tmp); cudaFree(scan_tmp); cudaFree(nodes); cudaFree(d_sah);
+    lj_dev_free(prims_unsorted); lj_dev_free(prims_sorted); lj_dev_free(prims); lj_dev_free(boxes);
+    lj_dev_free(tree.box); lj_dev_free(tree.left); lj_dev_free(tree.right); lj_dev_free(tree.count);
+    lj_dev_free(scene_bounds); lj_dev_free(cluster_a); lj_dev_free(cluster_b); lj_dev_free(cluster_tmp); lj_dev_free(nearest);
+    lj_dev_free(keep); lj_dev_free(offset); lj_dev_free(d_ints);
+    lj_dev_free(keys); lj_dev_free(keys_sorted); lj_dev_free(vals); lj_dev_free(vals_sorted);
+    lj_dev_free(queue_a); lj_dev_free(queue_b);
+    lj_dev_free(cub_tmp); lj_dev_free(scan_tmp); lj_dev_free(nodes); lj_dev_free(d_sah);
     return err;
 }
 

@@ -29,4 +29,9 @@ __device__ __forceinline__ double lj_warp_sum(double x) {
     return x;
 }
 __device__ __forceinline__ int lj_float_as_int(float f) { return __float_as_int(f); }
+// Scene tables and BVH-build temporaries (~60 blocks per scene) come from the device's stream-ordered pool, whose
+// release threshold lj_init raises so freed blocks stay cached: a scene-per-render caller otherwise pays a
+// device-wide synchronisation and an unmap for every cudaFree (measured: 0.05-0.6 s per sponza scene).
+inline cudaError_t lj_dev_alloc(void **p, size_t bytes) { return cudaMallocAsync(p, bytes, (cudaStream_t)0); }
+inline cudaError_t lj_dev_free(void *p) { return p ? cudaFreeAsync(p, (cudaStream_t)0) : cudaSuccess; }
 #endif

@@ -3,6 +3,8 @@
 // shape + light sampling tables, light power table) and make_mipmap (mipmap.h:24-48), for HBM.
 #include "scene.cuh"
 
+#include <mutex>
+
 #include <math.h>
 #include <string.h>
 
@@ -48,7 +50,7 @@ struct Uploader {
     T *alloc(size_t n) {
         void *p = nullptr;
         size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
-        cudaError_t e = cudaMalloc(&p, bytes);
+        cudaError_t e = lj_dev_alloc(&p, bytes);
         if (e != cudaSuccess) { if (err == cudaSuccess) err = e; return nullptr; }
         s->allocations.push_back(p);
         s->info.device_bytes += (int64_t)bytes;
@@ -105,6 +107,38 @@ DevVolume conv_volume(const lj_volume_desc &v, Uploader &up) {
 
 using namespace lj;
 
+namespace lj {
+namespace {
+std::mutex g_pool_mutex;
+struct CachedBlock { int device; void *block; size_t bytes; };
+CachedBlock g_cached = {-1, nullptr, 0};  // at most one spare block per process
+}  // namespace
+void *pool_block_take(int device, size_t bytes, size_t *got_bytes) {
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mutex);
+        if (g_cached.block && g_cached.device == device && g_cached.bytes >= bytes && g_cached.bytes <= 2 * bytes) {
+            void *b = g_cached.block;
+            *got_bytes = g_cached.bytes;
+            g_cached.block = nullptr;
+            return b;
+        }
+    }
+    void *b = nullptr;
+    if (cudaMalloc(&b, bytes) != cudaSuccess) return nullptr;
+    *got_bytes = bytes;
+    return b;
+}
+void pool_block_give(int device, void *block, size_t bytes) {
+    void *old = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mutex);
+        old = g_cached.block;
+        g_cached = {device, block, bytes};
+    }
+    if (old) cudaFree(old);
+}
+}  // namespace lj
+
 extern "C" const char *lj_last_error(void) { return g_error.c_str(); }
 
 extern "C" int lj_init(int device) {
@@ -118,13 +152,24 @@ extern "C" int lj_init(int device) {
     if (device < 0 || device >= count) { set_error("device index out of range"); return LJ_ERR_INVALID; }
     LJ_CUDA(cudaSetDevice(device));
     LJ_CUDA(cudaFree(0));
+#if !defined(LJ_HOSTSIM)
+    {   // keep freed blocks in the stream-ordered pool (see lj_dev_alloc)
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
+#endif
     return LJ_OK;
 }
 
 extern "C" void lj_scene_destroy(lj_scene *s) {
     if (!s) return;
-    for (void *p : s->allocations) cudaFree(p);
-    if (s->pool_block) cudaFree(s->pool_block);
+    cudaDeviceSynchronize();  // the caller's streams may still read the tables
+    for (void *p : s->allocations) lj_dev_free(p);
+    if (s->pool_block) pool_block_give(s->device, s->pool_block, s->pool_bytes);
     if (s->d_film) cudaFree(s->d_film);
     if (s->d_film_sq) cudaFree(s->d_film_sq);
     for (cudaEvent_t e : s->event_pool) cudaEventDestroy(e);

@@ -21,6 +21,7 @@ struct lj_scene {
     // persistent path pool (allocated on first render, reused)
     lj::PathPool pool;
     void *pool_block = nullptr;
+    size_t pool_bytes = 0;
     int pool_capacity = 0;
     float *d_film = nullptr;    // w*h*4 fp32: sum rgb, sample count
     float *d_film_sq = nullptr; // w*h*4 fp32: sum of squares rgb
@@ -33,6 +34,10 @@ struct lj_scene {
 };
 
 namespace lj {
+// Path-pool blocks (0.6-0.9 GB) are recycled across scenes of one process: a cudaMalloc / cudaFree pair of that size
+// stalls the host for up to 100 ms now and then, which a render-per-scene caller pays on every call.
+void *pool_block_take(int device, size_t bytes, size_t *got_bytes);
+void pool_block_give(int device, void *block, size_t bytes);
 void set_error(const std::string &msg);
 int cuda_fail(cudaError_t e, const char *what);
 }  // namespace lj

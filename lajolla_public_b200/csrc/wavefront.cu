@@ -17,6 +17,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <chrono>
 #include <vector>
 
 namespace lj {
@@ -591,9 +592,10 @@ __global__ void __launch_bounds__(128) k_aux(const LJ_GRID_CONSTANT DevScene sc,
 
 static int ensure_pool(lj_scene *s, int capacity, bool vol) {
     if (s->pool_capacity == capacity && s->pool_block && (s->pool.vol0 != nullptr) == vol) return LJ_OK;
-    if (s->pool_block) { cudaFree(s->pool_block); s->pool_block = nullptr; }
+    if (s->pool_block) { pool_block_give(s->device, s->pool_block, s->pool_bytes); s->pool_block = nullptr; }
     const int kFields = vol ? 14 : 9;
-    LJ_CUDA(cudaMalloc(&s->pool_block, (size_t)capacity * sizeof(V4) * kFields + (size_t)capacity / LJ_WARP_WIDTH * sizeof(uint32_t)));
+    s->pool_block = pool_block_take(s->device, (size_t)capacity * sizeof(V4) * kFields + (size_t)capacity / LJ_WARP_WIDTH * sizeof(uint32_t), &s->pool_bytes);
+    if (!s->pool_block) { s->pool_capacity = 0; return cuda_fail(cudaErrorMemoryAllocation, "path pool allocation"); }
     V4 *base = (V4 *)s->pool_block;
     PathPool &p = s->pool;
     p.ray_o = base + (size_t)capacity * 0; p.ray_d = base + (size_t)capacity * 1; p.hit = base + (size_t)capacity * 2;
@@ -653,6 +655,8 @@ static int render_impl(lj_scene *s, const lj_render_opts *opts_in, float *d_out,
         unsigned long long want = (unsigned long long)npix * (unsigned)(se - sb);
         if (want < (unsigned long long)capacity) capacity = (int)((want + 255) / 256 * 256);
     }
+    const bool host_prof = getenv("LJ_PROFILE_HOST") != nullptr;  // host-side phase times on stderr
+    auto hp_t0 = std::chrono::steady_clock::now();
     int r = ensure_pool(s, capacity, vol);
     if (r != LJ_OK) return r;
     if (!s->d_film) LJ_CUDA(cudaMalloc(&s->d_film, (size_t)npix * 16));
@@ -660,6 +664,7 @@ static int render_impl(lj_scene *s, const lj_render_opts *opts_in, float *d_out,
     if (!s->d_counters) LJ_CUDA(cudaMalloc(&s->d_counters, sizeof(unsigned long long) * C_TOTAL));
     if (!s->h_counters) LJ_CUDA(cudaMallocHost(&s->h_counters, sizeof(unsigned long long) * (C_TOTAL + 8)));
     if (!s->d_cursors) LJ_CUDA(cudaMalloc(&s->d_cursors, 4 * sizeof(unsigned int)));
+    auto hp_t1 = std::chrono::steady_clock::now();
     unsigned long long *d_counters = s->d_counters;
     unsigned long long *h_counters = s->h_counters;  // C_COUNT final counters, then the ring of per-wave live-path counts
     unsigned long long *h_active = h_counters + C_TOTAL;
@@ -771,12 +776,19 @@ static int render_impl(lj_scene *s, const lj_render_opts *opts_in, float *d_out,
         marks.push_back(e0); marks.push_back(e1); marks.push_back(e2); marks.push_back(e3); marks.push_back(e4);
         if (queued > 1000000) { set_error("wavefront loop did not terminate"); return LJ_ERR_CUDA; }
     }
+    auto hp_t2 = std::chrono::steady_clock::now();
     LJ_CUDA(cudaEventRecord(ev_end, stream));
     LJ_LAUNCH(k_resolve, (npix + 255) / 256, 256, stream, s->d_film, a.film_sq, npix, 1.f / (float)(se - sb), opts.normalize, d_out, d_var);
     launches++;
     LJ_CUDA(cudaMemcpyAsync(h_counters, d_counters, sizeof(unsigned long long) * C_TOTAL, cudaMemcpyDeviceToHost, stream));
     LJ_CUDA(cudaStreamSynchronize(stream));
     LJ_CUDA(cudaGetLastError());
+    auto hp_t3 = std::chrono::steady_clock::now();
+    if (host_prof) {
+        auto ms_ = [](auto a_, auto b_) { return std::chrono::duration<double, std::milli>(b_ - a_).count(); };
+        fprintf(stderr, "lj_render host: alloc %.2f ms, queue loop %.2f ms, drain %.2f ms, events %zu\n", ms_(hp_t0, hp_t1), ms_(hp_t1, hp_t2),
+                ms_(hp_t2, hp_t3), s->event_pool.size());
+    }
     if (stats) {
         memset(stats, 0, sizeof(*stats));
         float ms = 0;
@@ -822,17 +834,27 @@ extern "C" int lj_render_device(lj_scene *s, const lj_render_opts *opts, float *
 extern "C" int lj_render(lj_scene *s, const lj_render_opts *opts, float *out_rgb, lj_stats *stats) {
     if (!s || !out_rgb) { set_error("null argument"); return LJ_ERR_INVALID; }
     int npix = s->dev.camera.width * s->dev.camera.height;
+    const bool host_prof = getenv("LJ_PROFILE_HOST") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
     float *d_out = nullptr, *d_var = nullptr;
-    LJ_CUDA(cudaMalloc(&d_out, (size_t)npix * 3 * sizeof(float)));
+    LJ_CUDA(lj_dev_alloc((void **)&d_out, (size_t)npix * 3 * sizeof(float)));
     bool want_var = opts && opts->variance_out;
-    if (want_var) LJ_CUDA(cudaMalloc(&d_var, (size_t)npix * 3 * sizeof(float)));
+    if (want_var) LJ_CUDA(lj_dev_alloc((void **)&d_var, (size_t)npix * 3 * sizeof(float)));
+    auto t1 = std::chrono::steady_clock::now();
     int r = render_impl(s, opts, d_out, d_var, s->stream, stats);
+    auto t2 = std::chrono::steady_clock::now();
     if (r == LJ_OK) {
         cudaError_t e = cudaMemcpy(out_rgb, d_out, (size_t)npix * 3 * sizeof(float), cudaMemcpyDeviceToHost);
         if (e == cudaSuccess && want_var) e = cudaMemcpy(opts->variance_out, d_var, (size_t)npix * 3 * sizeof(float), cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) r = cuda_fail(e, "framebuffer download");
     }
-    cudaFree(d_out);
-    if (d_var) cudaFree(d_var);
+    auto t3 = std::chrono::steady_clock::now();
+    lj_dev_free(d_out);
+    if (d_var) lj_dev_free(d_var);
+    if (host_prof) {
+        auto ms_ = [](auto a_, auto b_) { return std::chrono::duration<double, std::milli>(b_ - a_).count(); };
+        fprintf(stderr, "lj_render: out alloc %.2f ms, render_impl %.2f ms, download %.2f ms, free %.2f ms\n", ms_(t0, t1), ms_(t1, t2), ms_(t2, t3),
+                ms_(t3, std::chrono::steady_clock::now()));
+    }
     return r;
 }
