@@ -42,7 +42,7 @@ def test_scene_tables(oracle, name):
     pc.check_light_table(sc, ref)
 
 
-@pytest.mark.parametrize("name", SCENES)
+@pytest.mark.parametrize("name", SCENES + ["disney_bsdf", "vol_cbox_teapot", "hetvol"])
 def test_ray_parity(oracle, name):
     """Parity test 1 of north_star: same primitive for >= 99.99 % of rays, t within 1e-5 relative."""
     sc, ref = pair(oracle, name)
