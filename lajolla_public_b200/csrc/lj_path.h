@@ -110,6 +110,7 @@ LJ_HD float mis_power(float pa, float pb) { return (pa * pa) / (pa * pa + pb * p
 
 // One shade step of the surface path tracer.  On return: s.flags has kAlive iff an extension ray
 // was written; s.sh_tfar >= 0 iff a shadow ray was written.
+template <bool CALLS>
 LJ_HD void shade_path(const DevScene &sc, const RenderParams &rp, PathState &s, ShadeCounters &cnt) {
     Pcg rng = path_rng(s, rp);
     const bool primary = s.pdf_sa < 0;
@@ -194,9 +195,9 @@ LJ_HD void shade_path(const DevScene &sc, const RenderParams &rp, PathState &s, 
         }
         float p1 = light_pmf(sc, light_id) * pdf_point_on_light(sc, light, pl, vx.position);
         if (G > 0 && p1 > 0) {
-            V3 f = bsdf_eval(sc, mat, dir_view, dir_light, vx, 0);
+            V3 f = CALLS ? bsdf_eval_call(sc, mat, dir_view, dir_light, vx, 0) : bsdf_eval(sc, mat, dir_view, dir_light, vx, 0);
             V3 Le = light_emission(sc, light, -dir_light, 0.f, pl);
-            float p2 = bsdf_pdf(sc, mat, dir_view, dir_light, vx) * G;
+            float p2 = (CALLS ? bsdf_pdf_call(sc, mat, dir_view, dir_light, vx) : bsdf_pdf(sc, mat, dir_view, dir_light, vx)) * G;
             float w1 = mis_power(p1, p2);
             V3 c = s.T * (f * Le) * (G / p1 * w1);
             if (max3(c) > 0 || min3(c) < 0 || c.x != c.x || c.y != c.y || c.z != c.z) {
@@ -212,7 +213,7 @@ LJ_HD void shade_path(const DevScene &sc, const RenderParams &rp, PathState &s, 
     float bu = pcg_uniform(rng), bv = pcg_uniform(rng), bw = pcg_uniform(rng);
     s.rng_state = rng.state;
     BsdfSample bs;
-    if (!bsdf_sample(sc, mat, dir_view, vx, mk2(bu, bv), bw, bs)) { cnt.finished++; return; }
+    if (!(CALLS ? bsdf_sample_call(sc, mat, dir_view, vx, mk2(bu, bv), bw, bs) : bsdf_sample(sc, mat, dir_view, vx, mk2(bu, bv), bw, bs))) { cnt.finished++; return; }
     // ray_diff.radius stays 0 for the whole path upstream (only .spread is updated, :227-230)
     if (bs.eta == 0) {
         s.spread = spread_reflect(0.f, s.spread, vx.mean_curvature, bs.roughness);
@@ -220,8 +221,8 @@ LJ_HD void shade_path(const DevScene &sc, const RenderParams &rp, PathState &s, 
         s.spread = spread_refract(0.f, s.spread, vx.mean_curvature, bs.eta, bs.roughness);
         s.eta_scale /= (bs.eta * bs.eta);
     }
-    V3 f = bsdf_eval(sc, mat, dir_view, bs.dir_out, vx, 0);
-    float p2 = bsdf_pdf(sc, mat, dir_view, bs.dir_out, vx);
+    V3 f = CALLS ? bsdf_eval_call(sc, mat, dir_view, bs.dir_out, vx, 0) : bsdf_eval(sc, mat, dir_view, bs.dir_out, vx, 0);
+    float p2 = CALLS ? bsdf_pdf_call(sc, mat, dir_view, bs.dir_out, vx) : bsdf_pdf(sc, mat, dir_view, bs.dir_out, vx);
     if (!(p2 > 0)) { cnt.finished++; return; }
     s.rr_prob = fminf(max3(s.T) / s.eta_scale, 0.95f);  // :313, evaluated with the pre-update throughput
     s.T = s.T * f / p2;

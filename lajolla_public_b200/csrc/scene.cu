@@ -501,6 +501,7 @@ extern "C" int lj_scene_create(const lj_scene_desc *desc, lj_scene **out) {
             m.density = conv_volume(md.density, up);
         }
     }
+    for (int i = 0; i < desc->num_materials; i++) if (desc->materials[i].type >= LJ_MAT_DISNEY_DIFFUSE) s->has_disney = true;
     sc.media = up.upload(media);
     sc.num_media = desc->num_media;
     if (up.err != cudaSuccess) { int r = cuda_fail(up.err, "table upload"); lj_scene_destroy(s); return r; }

@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(128, MODE >= 2 ? LJ_WALK_MIN_BLOCKS : (MODE ==
 }
 
 // K4
-template <int MIN_BLOCKS>
+template <int MIN_BLOCKS, bool CALLS>
 __global__ void __launch_bounds__(128, MIN_BLOCKS) k_shade(const LJ_GRID_CONSTANT DevScene sc, const LJ_GRID_CONSTANT WaveArgs a) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     ShadeCounters cnt = {0, 0, 0, 0};
@@ -404,7 +404,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_shade(const LJ_GRID_CONSTAN
             const bool trace = dbg && (uint32_t)atoi(dbg) == s.pixel;
             V3 T0 = s.T, L0 = s.L, o0 = s.o, d0 = s.d;
 #endif
-            shade_path(sc, a.rp, s, cnt);
+            shade_path<CALLS>(sc, a.rp, s, cnt);
 #if defined(LJ_HOSTSIM)
             if (trace) fprintf(stderr, "RAY %.9g %.9g %.9g %.9g %.9g %.9g OUT %.9g %.9g %.9g\n", o0.x, o0.y, o0.z, d0.x, d0.y, d0.z, s.d.x, s.d.y, s.d.z);
             if (trace)
@@ -695,8 +695,7 @@ static int render_impl(lj_scene *s, const lj_render_opts *opts_in, float *d_out,
     if (const char *e = getenv("LJ_TRAV_MIN")) a.trav_min = std::max(1, atoi(e));
     a.chunk = 64;
     if (const char *e = getenv("LJ_CHUNK")) a.chunk = std::max(32, atoi(e));
-    int shade_occ = 4;  // resident CTAs per SM the shade kernel is compiled for (register cap), LJ_SHADE_OCC for tuning runs
-    if (const char *e = getenv("LJ_SHADE_OCC")) shade_occ = atoi(e);
+    // (k_shade is compiled for 4 resident CTAs per SM, 124 registers: caps of 5 / 6 / 8 CTAs spilled and were slower)
 
     const int nb256 = (capacity + 255) / 256, nb128 = (capacity + 127) / 128;
     // persistent grid: exactly one wave of resident CTAs (SM count x the occupancy of k_trace)
@@ -760,11 +759,10 @@ static int render_impl(lj_scene *s, const lj_render_opts *opts_in, float *d_out,
         if (vol) {
             if (sc.num_media > 0) { LJ_LAUNCH(k_flight, flight_blocks, 128, stream, sc, a); launches++; }
             LJ_LAUNCH(k_shade_vol, nb128, 128, stream, sc, a);
-        } else switch (shade_occ) {
-            case 5: LJ_LAUNCH(k_shade<5>, nb128, 128, stream, sc, a); break;
-            case 6: LJ_LAUNCH(k_shade<6>, nb128, 128, stream, sc, a); break;
-            case 8: LJ_LAUNCH(k_shade<8>, nb128, 128, stream, sc, a); break;
-            default: LJ_LAUNCH(k_shade<4>, nb128, 128, stream, sc, a); break;
+        } else if (s->has_disney) {
+            LJ_LAUNCH((k_shade<4, true>), nb128, 128, stream, sc, a);
+        } else {
+            LJ_LAUNCH((k_shade<4, false>), nb128, 128, stream, sc, a);
         }
         LJ_CUDA(cudaEventRecord(e3, stream));
         if (vol && s->has_grid_media) LJ_LAUNCH(k_trace<3>, step_blocks, 128, stream, sc, a);
