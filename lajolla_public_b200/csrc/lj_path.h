@@ -173,6 +173,10 @@ LJ_HD void shade_path(const DevScene &sc, const RenderParams &rp, PathState &s, 
     cnt.bounces++;
     if (vx.material_id < 0) { cnt.finished++; s.rng_state = rng.state; return; }  // reference asserts (:165)
     const DevMaterial &mat = sc.materials[vx.material_id];
+    // Lambertian fast path: the reflectance texture is fetched once per vertex instead of once per eval() call
+    // (material.cpp evaluates it inside each of eval / pdf / sample; same values, lambertian.inl:1-50)
+    const bool lambert = mat.type == LJ_MAT_LAMBERTIAN;
+    const V3 lambert_R = lambert ? mat_tex3(sc, mat, 0, vx) : mk3(0);
 
     // ---- next event estimation, :94-207
     float lu = pcg_uniform(rng), lv = pcg_uniform(rng);
@@ -195,9 +199,11 @@ LJ_HD void shade_path(const DevScene &sc, const RenderParams &rp, PathState &s, 
         }
         float p1 = light_pmf(sc, light_id) * pdf_point_on_light(sc, light, pl, vx.position);
         if (G > 0 && p1 > 0) {
-            V3 f = CALLS ? bsdf_eval_call(sc, mat, dir_view, dir_light, vx, 0) : bsdf_eval(sc, mat, dir_view, dir_light, vx, 0);
+            V3 f = lambert ? lambertian_eval(lambert_R, vx, dir_view, dir_light)
+                           : (CALLS ? bsdf_eval_call(sc, mat, dir_view, dir_light, vx, 0) : bsdf_eval(sc, mat, dir_view, dir_light, vx, 0));
             V3 Le = light_emission(sc, light, -dir_light, 0.f, pl);
-            float p2 = (CALLS ? bsdf_pdf_call(sc, mat, dir_view, dir_light, vx) : bsdf_pdf(sc, mat, dir_view, dir_light, vx)) * G;
+            float p2 = (lambert ? lambertian_pdf(vx, dir_view, dir_light)
+                                : (CALLS ? bsdf_pdf_call(sc, mat, dir_view, dir_light, vx) : bsdf_pdf(sc, mat, dir_view, dir_light, vx))) * G;
             float w1 = mis_power(p1, p2);
             V3 c = s.T * (f * Le) * (G / p1 * w1);
             if (max3(c) > 0 || min3(c) < 0 || c.x != c.x || c.y != c.y || c.z != c.z) {
@@ -213,7 +219,8 @@ LJ_HD void shade_path(const DevScene &sc, const RenderParams &rp, PathState &s, 
     float bu = pcg_uniform(rng), bv = pcg_uniform(rng), bw = pcg_uniform(rng);
     s.rng_state = rng.state;
     BsdfSample bs;
-    if (!(CALLS ? bsdf_sample_call(sc, mat, dir_view, vx, mk2(bu, bv), bw, bs) : bsdf_sample(sc, mat, dir_view, vx, mk2(bu, bv), bw, bs))) { cnt.finished++; return; }
+    if (!(lambert ? lambertian_sample(vx, dir_view, mk2(bu, bv), bs)
+                  : (CALLS ? bsdf_sample_call(sc, mat, dir_view, vx, mk2(bu, bv), bw, bs) : bsdf_sample(sc, mat, dir_view, vx, mk2(bu, bv), bw, bs)))) { cnt.finished++; return; }
     // ray_diff.radius stays 0 for the whole path upstream (only .spread is updated, :227-230)
     if (bs.eta == 0) {
         s.spread = spread_reflect(0.f, s.spread, vx.mean_curvature, bs.roughness);
@@ -221,8 +228,10 @@ LJ_HD void shade_path(const DevScene &sc, const RenderParams &rp, PathState &s, 
         s.spread = spread_refract(0.f, s.spread, vx.mean_curvature, bs.eta, bs.roughness);
         s.eta_scale /= (bs.eta * bs.eta);
     }
-    V3 f = CALLS ? bsdf_eval_call(sc, mat, dir_view, bs.dir_out, vx, 0) : bsdf_eval(sc, mat, dir_view, bs.dir_out, vx, 0);
-    float p2 = CALLS ? bsdf_pdf_call(sc, mat, dir_view, bs.dir_out, vx) : bsdf_pdf(sc, mat, dir_view, bs.dir_out, vx);
+    V3 f = lambert ? lambertian_eval(lambert_R, vx, dir_view, bs.dir_out)
+                   : (CALLS ? bsdf_eval_call(sc, mat, dir_view, bs.dir_out, vx, 0) : bsdf_eval(sc, mat, dir_view, bs.dir_out, vx, 0));
+    float p2 = lambert ? lambertian_pdf(vx, dir_view, bs.dir_out)
+                       : (CALLS ? bsdf_pdf_call(sc, mat, dir_view, bs.dir_out, vx) : bsdf_pdf(sc, mat, dir_view, bs.dir_out, vx));
     if (!(p2 > 0)) { cnt.finished++; return; }
     s.rr_prob = fminf(max3(s.T) / s.eta_scale, 0.95f);  // :313, evaluated with the pre-update throughput
     s.T = s.T * f / p2;
