@@ -7,8 +7,11 @@ BASELINE.json configs[3]: scenes/sponza/sponza.xml, 768x575, path integrator, 10
   value  : whole-job Msamples/s with the scene resident in HBM (lj_render_device into device memory)
   e2e    : the same through the host-buffer C ABI: lj_scene_create (H2D of the flat scene + GPU BVH/mip
            build) + lj_render (D2H of the w*h*3 fp32 image) inside the timed region
-  N > 1  : one process per GPU (torchrun); every rank renders the full spp budget with disjoint PCG
-           stream ids (weak scaling: per-GPU work fixed), then one NCCL sum-reduce of the fp32 film.
+  N > 1  : one process per GPU (torchrun).  Default "strong" scaling: the image and its sample count are FIXED
+           (BASELINE config 4: sponza at 1024 spp on 1/2/4/8 GPUs); rank r renders its contiguous block of the
+           per-pixel sample indices (--split spp, default) or its interleaved share of the 8x4-pixel tiles
+           (--split tiles), then one NCCL sum-reduce of the fp32 film.  --scaling weak keeps the per-GPU
+           sample count fixed instead (image spp grows with N).
   --impl reference : lajolla's own CPU render() (unmodified reference objects + the Embree-API shim,
            oracle/_ref) on the host cores, on a bounded spp sample of the same scene.
 Prints ONE JSON line on rank 0.
@@ -170,6 +173,8 @@ def main():
     ap.add_argument("--cpu-spp", type=int, default=0)
     ap.add_argument("--pool", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--split", default="spp", choices=["spp", "tiles"])
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -200,18 +205,27 @@ def main():
     info = scene.info()
     w, h = scene.width, scene.height
     npix = w * h
-    total_spp = spp * world
+    strong = args.scaling == "strong"
+    total_spp = spp if strong else spp * world
     film = torch.zeros((h, w, 3), dtype=torch.float32, device="cuda")
     stream = torch.cuda.Stream()  # a non-blocking stream of our own: the legacy default stream serialises against every other stream
     torch.cuda.set_stream(stream)
 
     from lajolla_public_b200 import partition
-    _, s_begin, s_end = partition.weak_range(rank, world, spp)
+    tile_stride, tile_offset = 0, 0
+    if args.split == "tiles" and world > 1:
+        s_begin, s_end = 0, total_spp              # every sample of this rank's interleaved tiles
+        tile_stride, tile_offset = world, rank
+    elif strong:
+        s_begin, s_end = partition.sample_ranges(total_spp, world)[rank]
+    else:
+        _, s_begin, s_end = partition.weak_range(rank, world, spp)
 
     def step():
-        # every rank renders its own spp block of the (spp * world)-sample image
+        # every rank renders its share of the total_spp-sample image into its own film (raw sums)
         st = scene.render_device(film.data_ptr(), stream.cuda_stream, spp=total_spp, sample_begin=s_begin,
-                                 sample_end=s_end, normalize=False, pool_paths=args.pool)
+                                 sample_end=s_end, normalize=False, pool_paths=args.pool,
+                                 tile_stride=tile_stride, tile_offset=tile_offset)
         partition.reduce_film(film, dist, 0)  # the one collective
         return st
 
@@ -227,7 +241,7 @@ def main():
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     agg = {"extend_ms": 0.0, "shadow_ms": 0.0, "shade_ms": 0.0, "regen_ms": 0.0, "render_ms": 0.0, "closest": 0, "shadow": 0,
-           "bounces": 0, "launches": 0, "extend_launches": 0, "samples": 0, "waves": 0, "node_steps": 0, "prim_tests": 0}
+           "bounces": 0, "launches": 0, "extend_launches": 0, "samples": 0, "waves": 0, "node_steps": 0, "prim_tests": 0, "node_passes": 0, "prim_passes": 0}
     e0.record(stream)
     for _ in range(args.steps):
         st = step()
@@ -237,6 +251,7 @@ def main():
         agg["launches"] += st.kernel_launches + (1 if dist is not None else 0)
         agg["extend_launches"] += st.extend_launches; agg["samples"] += st.samples; agg["waves"] += st.waves
         agg["node_steps"] += st.node_steps; agg["prim_tests"] += st.prim_tests
+        agg["node_passes"] += st.node_passes; agg["prim_passes"] += st.prim_passes
     e1.record(stream)
     barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
@@ -257,7 +272,8 @@ def main():
         ta = time.perf_counter()
         sc2 = lj.Scene(desc, device=local_rank)
         tb = time.perf_counter()
-        img = sc2.render(spp=total_spp, sample_begin=rank * spp, sample_end=(rank + 1) * spp, normalize=True, pool_paths=args.pool)
+        img = sc2.render(spp=total_spp, sample_begin=s_begin, sample_end=s_end, normalize=True, pool_paths=args.pool,
+                         tile_stride=tile_stride, tile_offset=tile_offset)
         tc = time.perf_counter()
         e2e_parts["device_render_ms"] += sc2.last_stats.render_ms / e2e_steps
         sc2.close()
@@ -267,40 +283,33 @@ def main():
     e2e_s = torch.tensor([time.perf_counter() - t0], device="cuda")
     if dist is not None:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = npix * spp * world * e2e_steps / float(e2e_s.item()) / 1e6
+    e2e_value = npix * total_spp * e2e_steps / float(e2e_s.item()) / 1e6
 
     # L2-side bound: BVH nodes and primitives are L2-resident; measured L2 copy bandwidth of this GPU
     # (two 24 MB buffers, both inside the 126 MB L2) against the bytes the traversal kernels fetch, counted live.
-    l2_peak = None
+    l2_peak = hbm_read = None
     if rank == 0:
-        xa = torch.empty(6 << 20, dtype=torch.float32, device="cuda"); xb = torch.empty_like(xa)
-        for _ in range(5):
-            xb.copy_(xa)
-        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0.record(stream)
-        for _ in range(50):
-            xb.copy_(xa)
-        l1.record(stream)
-        torch.cuda.synchronize()
-        l2_peak = 2 * xa.numel() * 4 * 50 / (l0.elapsed_time(l1) / 1e3) / 1e9
-        del xa, xb
+        l2_peak = lj.measure_read_bandwidth(32 << 20, 200)    # 32 MB working set, L2-resident
+        hbm_read = lj.measure_read_bandwidth(4 << 30, 3)      # 4 GB, streams from HBM
     if rank == 0:
         peak, peak_kind = load_peaks()
-        value = npix * spp * world * args.steps / (ms_total / 1e3) / 1e6
+        value = npix * total_spp * args.steps / (ms_total / 1e3) / 1e6
         ext_bytes = BYTES_PER_EXTENSION_RAY * agg["closest"]
         achieved = ext_bytes / (agg["extend_ms"] / 1e3) / 1e9 if agg["extend_ms"] > 0 else 0.0
         line = {
             "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(key, w, h, full_spp), "spp_per_gpu": spp, "image_spp": total_spp,
+            "config": {"workload": workload_name(key, w, h, full_spp), "spp_per_gpu": (s_end - s_begin) if tile_stride == 0 else total_spp, "image_spp": total_spp,
                        "l2_policy": f"path pool (4M slots x {224 if key in VOLPATH else 144} B) streams through HBM every wave, larger than the 126 MB L2",
-                       "scene_source": "reference scene flattened to .ljs", "parallelism": f"spp-split x{world} + NCCL reduce"},
+                       "scene_source": "reference scene flattened to .ljs", "parallelism": f"{args.split}-split x{world} + NCCL reduce" if world > 1 else "single GPU"},
             "mrays_per_s": (agg["closest"] + agg["shadow"]) * world / (ms_total / 1e3) / 1e6,
             "rays_per_sample": (agg["closest"] + agg["shadow"]) / max(agg["samples"], 1),
             "mean_bounces": agg["bounces"] / max(agg["samples"], 1),
             "node_steps_per_ray": agg["node_steps"] / max(agg["closest"] + agg["shadow"], 1),
             "prim_tests_per_ray": agg["prim_tests"] / max(agg["closest"] + agg["shadow"], 1),
+            "simd_efficiency": {"node_step": agg["node_steps"] / max(32 * agg["node_passes"], 1), "prim_step": agg["prim_tests"] / max(32 * agg["prim_passes"], 1),
+                                "note": "lanes doing the step / 32, per warp pass of the traversal kernels (counted by the kernels)"},
             "stage_ms_per_step": {k: agg[k] / args.steps for k in ("regen_ms", "extend_ms", "shade_ms", "shadow_ms", "render_ms")},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": int(cdesc_bytes),
@@ -313,7 +322,8 @@ def main():
                          "rays_per_launch": agg["closest"] / max(agg["extend_launches"], 1),
                          "avg_launch_ms": agg["extend_ms"] / max(agg["extend_launches"], 1)},
             "roofline_l2": {"bound": "l2", "kernel": "k_trace<0> + k_trace<1|2|3>", "unit": "GB/s", "peak": l2_peak,
-                            "peak_kind": "measured here: torch copy of 24 MB <-> 24 MB, L2-resident",
+                            "peak_kind": "measured here: read-only 16-byte-load stream over a 32 MB working set, all SMs (lj_measure_read_bandwidth)",
+                            "hbm_read_gbs_same_probe": hbm_read,
                             "achieved": (agg["node_steps"] * 80 + agg["prim_tests"] * 48) / max((agg["extend_ms"] + agg["shadow_ms"]) / 1e3, 1e-9) / 1e9,
                             "frac": (agg["node_steps"] * 80 + agg["prim_tests"] * 48) / max((agg["extend_ms"] + agg["shadow_ms"]) / 1e3, 1e-9) / 1e9 / l2_peak,
                             "bytes": "80 B per wide-node step + 48 B per primitive test, both counted by the kernels"},

@@ -163,10 +163,23 @@ typedef struct lj_render_opts {
     int32_t sample_begin;  /* this call renders samples [sample_begin, sample_end) of every pixel; */
     int32_t sample_end;    /* both 0 => [0, spp).  PCG stream of a path = hash(pixel*spp + sample)    */
     int32_t normalize;     /* 1: divide by (sample_end-sample_begin) like render.cpp:94; 0: raw sums */
-    int32_t pool_paths;    /* path slots resident in HBM; <=0: default (1<<22) */
+    int32_t pool_paths;    /* path slots resident in HBM (rounded up to a multiple of 256, at least 1024);
+                              0: sized to the work, at most 1<<22 */
     uint64_t seed;         /* 0 => pcg.h:33 default seed */
     float *variance_out;   /* optional host w*h*3: per-pixel sample variance of the mean (NULL to skip) */
+    /* Image-space share of this call (the reference's decomposition is image tiles, render.cpp:75-100): only the
+     * 8x4-pixel tiles t with t % tile_stride == tile_offset are rendered, the other pixels stay 0.
+     * tile_stride <= 1: the whole image. */
+    int32_t tile_stride, tile_offset;
+    /* lj_render only: GPUs to use (0: every device given to lj_init, 1: the scene's primary device) and how the work
+     * is split among them; the per-GPU films are summed on the primary device. */
+    int32_t num_gpus;
+    int32_t split;         /* LJ_SPLIT_* */
+    int32_t reduce;        /* LJ_REDUCE_* */
+    int32_t _pad;
 } lj_render_opts;
+enum { LJ_SPLIT_AUTO = 0, LJ_SPLIT_SPP = 1, LJ_SPLIT_TILES = 2 };
+enum { LJ_REDUCE_AUTO = 0, LJ_REDUCE_P2P = 1, LJ_REDUCE_NCCL = 2 };
 
 typedef struct lj_stats {
     double render_ms;          /* CUDA-event time of the wavefront loop (inputs resident) */
@@ -180,6 +193,11 @@ typedef struct lj_stats {
     uint64_t extend_launches, shadow_launches, shade_launches, regen_launches;
     uint64_t node_steps;       /* wide-node tests executed by both traversal kernels */
     uint64_t prim_tests;       /* ray/primitive tests executed by both traversal kernels */
+    uint64_t node_passes;      /* warp passes that ran a node step / a primitive step: steps / (32 * passes) is the */
+    uint64_t prim_passes;      /* SIMD efficiency of the traversal kernels */
+    uint64_t pool_paths;       /* path slots the call used */
+    int32_t gpus_used, _pad;
+    double reduce_ms;          /* multi-GPU: film reduction on the primary device */
 } lj_stats;
 
 /* Selects the CUDA device for the calling thread; LJ_ERR_NO_DEVICE if there is none. */
@@ -206,6 +224,22 @@ typedef struct lj_hit { float t, u, v; int32_t shape_id, primitive_id; } lj_hit;
 /* intersect() / occluded() (intersection.cpp:7-85), host buffers. */
 int lj_trace_closest(lj_scene *scene, const lj_ray *rays, int64_t n, lj_hit *hits, double *kernel_ms);
 int lj_trace_any(lj_scene *scene, const lj_ray *rays, int64_t n, uint8_t *occluded, double *kernel_ms);
+
+/* The same two queries with a choice of traversal code (parity tests of the kernels that render):
+ *   LJ_TRACE_PLAIN            one thread per ray, plain loop (what lj_trace_closest / lj_trace_any run)
+ *   LJ_TRACE_WAVEFRONT        the rays are loaded into the path pool and traced by the persistent queue kernels
+ *                             exactly as lj_render launches them for the path integrator (closest hit / NEE shadow)
+ *   LJ_TRACE_WAVEFRONT_LANE   same, through the one-ray-per-lane persistent kernels (the volpath integrator's)
+ * For the wavefront any-hit kernels rays[].tnear must equal the scene's shadow epsilon (lj_scene_info). */
+enum { LJ_TRACE_PLAIN = 0, LJ_TRACE_WAVEFRONT = 1, LJ_TRACE_WAVEFRONT_LANE = 2 };
+typedef struct lj_trace_opts {
+    int32_t kernel;      /* LJ_TRACE_* */
+    int32_t pool_paths;  /* path-pool slots (0: sized to the batch); batches larger than the pool run in rounds */
+    int32_t slot_stride; /* the rays occupy every slot_stride-th slot, the other slots hold no path (<= 1: dense) */
+    int32_t _pad;
+} lj_trace_opts;
+int lj_trace_closest_ex(lj_scene *scene, const lj_ray *rays, int64_t n, const lj_trace_opts *opts, lj_hit *hits, double *kernel_ms);
+int lj_trace_any_ex(lj_scene *scene, const lj_ray *rays, int64_t n, const lj_trace_opts *opts, uint8_t *occluded, double *kernel_ms);
 
 /* PathVertex as intersect() assembles it (intersection.h:15-35, intersection.cpp:37-62). */
 typedef struct lj_vertex {
@@ -283,6 +317,11 @@ int lj_scene_get_light_table(lj_scene *scene, float *pmf, float *cdf);
 /* One mip level of image `image_id` with `channels` in {1,3} (mipmap.h): returns dims; data may be NULL. */
 int lj_scene_get_mip_level(lj_scene *scene, int32_t channels, int32_t image_id, int32_t level,
                            int32_t *width, int32_t *height, float *data);
+
+/* Roofline denominators measured on the spot: GB/s of a read-only stream of 16-byte loads, all SMs, over a working
+ * set of `bytes` swept `iters` times (after a warm-up sweep).  A set that fits the 126 MB L2 gives the L2 read rate
+ * the BVH / primitive / texture fetches are bounded by; a much larger one gives HBM's. */
+int lj_measure_read_bandwidth(int64_t bytes, int32_t iters, double *gb_per_s);
 
 #ifdef __cplusplus
 }

@@ -88,8 +88,10 @@ class Scene:
             pass
 
     # ---- S1
-    def render(self, spp=0, sample_begin=0, sample_end=0, normalize=True, pool_paths=0, seed=0, variance=False):
-        opts = abi.lj_render_opts(spp, sample_begin, sample_end, 1 if normalize else 0, pool_paths, seed, None)
+    def render(self, spp=0, sample_begin=0, sample_end=0, normalize=True, pool_paths=0, seed=0, variance=False,
+               tile_stride=0, tile_offset=0, num_gpus=1, split=0, reduce=0):
+        opts = abi.lj_render_opts(spp, sample_begin, sample_end, 1 if normalize else 0, pool_paths, seed, None,
+                                  tile_stride, tile_offset, num_gpus, split, reduce, 0)
         out = np.empty((self.height, self.width, 3), dtype=np.float32)
         var = None
         if variance:
@@ -100,27 +102,33 @@ class Scene:
         self.last_stats = stats
         return (out, var) if variance else out
 
-    def render_device(self, d_out_ptr, stream_ptr=None, spp=0, sample_begin=0, sample_end=0, normalize=False, pool_paths=0, seed=0):
+    def render_device(self, d_out_ptr, stream_ptr=None, spp=0, sample_begin=0, sample_end=0, normalize=False, pool_paths=0, seed=0,
+                      tile_stride=0, tile_offset=0):
         """Render into DEVICE memory (w*h*3 fp32 at d_out_ptr) on the given cudaStream_t."""
-        opts = abi.lj_render_opts(spp, sample_begin, sample_end, 1 if normalize else 0, pool_paths, seed, None)
+        opts = abi.lj_render_opts(spp, sample_begin, sample_end, 1 if normalize else 0, pool_paths, seed, None,
+                                  tile_stride, tile_offset, 1, 0, 0, 0)
         stats = abi.lj_stats()
         abi.check(self._lib.lj_render_device(self._h, C.byref(opts), C.c_void_p(d_out_ptr), C.c_void_p(stream_ptr or 0), C.byref(stats)))
         self.last_stats = stats
         return stats
 
     # ---- S2
-    def intersect_hits(self, rays, want_ms=False):
+    def intersect_hits(self, rays, want_ms=False, kernel=abi.LJ_TRACE_PLAIN, pool_paths=0, slot_stride=1):
+        """rtcIntersect1-equivalent for a batch.  kernel: abi.LJ_TRACE_PLAIN (one thread per ray), LJ_TRACE_WAVEFRONT /
+        LJ_TRACE_WAVEFRONT_LANE (the persistent kernels of the renderer, rays loaded into the path pool)."""
         rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
         hits = np.zeros(rays.shape[0], dtype=HIT_DTYPE)
         ms = C.c_double(0)
-        abi.check(self._lib.lj_trace_closest(self._h, _ptr(rays, abi.lj_ray), rays.shape[0], _ptr(hits, abi.lj_hit), C.byref(ms)))
+        opts = abi.lj_trace_opts(kernel, pool_paths, slot_stride, 0)
+        abi.check(self._lib.lj_trace_closest_ex(self._h, _ptr(rays, abi.lj_ray), rays.shape[0], C.byref(opts), _ptr(hits, abi.lj_hit), C.byref(ms)))
         return (hits, ms.value) if want_ms else hits
 
-    def occluded(self, rays, want_ms=False):
+    def occluded(self, rays, want_ms=False, kernel=abi.LJ_TRACE_PLAIN, pool_paths=0, slot_stride=1):
         rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
         occ = np.zeros(rays.shape[0], dtype=np.uint8)
         ms = C.c_double(0)
-        abi.check(self._lib.lj_trace_any(self._h, _ptr(rays, abi.lj_ray), rays.shape[0], _ptr(occ, C.c_uint8), C.byref(ms)))
+        opts = abi.lj_trace_opts(kernel, pool_paths, slot_stride, 0)
+        abi.check(self._lib.lj_trace_any_ex(self._h, _ptr(rays, abi.lj_ray), rays.shape[0], C.byref(opts), _ptr(occ, C.c_uint8), C.byref(ms)))
         return (occ.astype(bool), ms.value) if want_ms else occ.astype(bool)
 
     def intersect(self, rays, ray_diff=None):
@@ -191,6 +199,14 @@ def pcg32(first_stream, n_streams, n_draws, seed=0):
     f = np.zeros((n_streams, n_draws), dtype=np.float32)
     abi.check(lib.lj_pcg32_batch(first_stream, seed, n_streams, n_draws, _ptr(u, C.c_uint32), _ptr(f, C.c_float)))
     return u, f
+
+
+def measure_read_bandwidth(nbytes, iters=20):
+    """GB/s of a read-only 16-byte-load stream over `nbytes` (<= L2: the L2 read rate; >> L2: HBM)."""
+    lib = load_library()
+    v = C.c_double(0)
+    abi.check(lib.lj_measure_read_bandwidth(int(nbytes), int(iters), C.byref(v)))
+    return v.value
 
 
 LAJOLLA_CLI = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lajolla")

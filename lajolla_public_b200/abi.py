@@ -72,7 +72,8 @@ class lj_scene_desc(C.Structure):
 
 class lj_render_opts(C.Structure):
     _fields_ = [("spp", i32), ("sample_begin", i32), ("sample_end", i32), ("normalize", i32), ("pool_paths", i32),
-                ("seed", u64), ("variance_out", pf32)]
+                ("seed", u64), ("variance_out", pf32), ("tile_stride", i32), ("tile_offset", i32),
+                ("num_gpus", i32), ("split", i32), ("reduce", i32), ("_pad", i32)]
 
 
 class lj_stats(C.Structure):
@@ -80,11 +81,19 @@ class lj_stats(C.Structure):
                 ("samples", u64), ("closest_rays", u64), ("shadow_rays", u64), ("bounces", u64),
                 ("kernel_launches", u64), ("waves", u64),
                 ("extend_launches", u64), ("shadow_launches", u64), ("shade_launches", u64), ("regen_launches", u64),
-                ("node_steps", u64), ("prim_tests", u64)]
+                ("node_steps", u64), ("prim_tests", u64), ("node_passes", u64), ("prim_passes", u64),
+                ("pool_paths", u64), ("gpus_used", i32), ("_pad", i32), ("reduce_ms", f64)]
 
 
 class lj_ray(C.Structure):
     _fields_ = [("org", f32 * 3), ("tnear", f32), ("dir", f32 * 3), ("tfar", f32)]
+
+
+class lj_trace_opts(C.Structure):
+    _fields_ = [("kernel", i32), ("pool_paths", i32), ("slot_stride", i32), ("_pad", i32)]
+
+
+LJ_TRACE_PLAIN, LJ_TRACE_WAVEFRONT, LJ_TRACE_WAVEFRONT_LANE = 0, 1, 2
 
 
 class lj_hit(C.Structure):
@@ -143,6 +152,8 @@ PROTOTYPES = {
     "lj_render_device": (C.c_int, [C.c_void_p, C.POINTER(lj_render_opts), C.c_void_p, C.c_void_p, C.POINTER(lj_stats)]),
     "lj_trace_closest": (C.c_int, [C.c_void_p, C.POINTER(lj_ray), i64, C.POINTER(lj_hit), C.POINTER(f64)]),
     "lj_trace_any": (C.c_int, [C.c_void_p, C.POINTER(lj_ray), i64, C.POINTER(u8), C.POINTER(f64)]),
+    "lj_trace_closest_ex": (C.c_int, [C.c_void_p, C.POINTER(lj_ray), i64, C.POINTER(lj_trace_opts), C.POINTER(lj_hit), C.POINTER(f64)]),
+    "lj_trace_any_ex": (C.c_int, [C.c_void_p, C.POINTER(lj_ray), i64, C.POINTER(lj_trace_opts), C.POINTER(u8), C.POINTER(f64)]),
     "lj_intersect": (C.c_int, [C.c_void_p, C.POINTER(lj_ray), pf32, i64, C.POINTER(lj_vertex)]),
     "lj_bsdf_batch": (C.c_int, [C.c_void_p, C.POINTER(lj_bsdf_query), i64, C.POINTER(lj_bsdf_result)]),
     "lj_light_batch": (C.c_int, [C.c_void_p, C.POINTER(lj_light_query), i64, C.POINTER(lj_light_result)]),
@@ -152,6 +163,7 @@ PROTOTYPES = {
     "lj_pcg32_batch": (C.c_int, [u64, u64, i32, i32, C.POINTER(u32), pf32]),
     "lj_scene_get_info": (C.c_int, [C.c_void_p, C.POINTER(lj_scene_info)]),
     "lj_scene_get_light_table": (C.c_int, [C.c_void_p, pf32, pf32]),
+    "lj_measure_read_bandwidth": (C.c_int, [i64, i32, C.POINTER(f64)]),
     "lj_scene_get_mip_level": (C.c_int, [C.c_void_p, i32, i32, i32, pi32, pi32, pf32]),
 }
 

@@ -5,6 +5,8 @@
 #include "scene.cuh"
 #include "lj_media.h"
 
+#include <algorithm>
+
 namespace lj {
 namespace {
 
@@ -17,21 +19,6 @@ struct DevBuf {
     cudaError_t up(const T *h, size_t n) { return cudaMemcpy(p, h, n * sizeof(T), cudaMemcpyHostToDevice); }
     cudaError_t down(T *h, size_t n) { return cudaMemcpy(h, p, n * sizeof(T), cudaMemcpyDeviceToHost); }
 };
-
-LJ_HD void hit_to_abi(const DevScene &sc, V3 org, V3 dir, const Hit &h, lj_hit &out) {
-    if (h.prim == kNoHit) { out.t = h.t; out.u = 0; out.v = 0; out.shape_id = -1; out.primitive_id = -1; return; }
-    V4 pc = ld4(&sc.prims[h.prim].c);
-    out.t = h.t;
-    out.shape_id = prim_shape_id(pc);
-    out.primitive_id = prim_primitive_id(pc);
-    if (prim_is_sphere(pc)) {
-        V4 pa = ld4(&sc.prims[h.prim].a);
-        V2 st = sphere_st((org + dir * h.t) - xyz(pa), pa.w);
-        out.u = st.x; out.v = st.y;
-    } else {
-        out.u = h.u; out.v = h.v;
-    }
-}
 
 __global__ void __launch_bounds__(256) k_trace_closest(const LJ_GRID_CONSTANT DevScene sc, const lj_ray *rays, long long n, lj_hit *hits) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -184,6 +171,25 @@ __global__ void k_pcg(uint64_t first_stream, uint64_t seed, int n_streams, int n
 
 int grid_for(long long n, int threads) { return (int)((n + threads - 1) / threads); }
 
+#if !defined(LJ_HOSTSIM)
+// read-only stream of 16-byte loads over a working set (roofline denominators measured on the spot)
+__global__ void __launch_bounds__(256) k_read_stream(const float4 *src, long long n16, int iters, float *sink) {
+    float acc = 0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (int it = 0; it < iters; it++) {
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += 4 * stride) {
+            // four independent loads in flight per thread
+            float4 a = src[i];
+            float4 b = i + stride < n16 ? src[i + stride] : make_float4(0, 0, 0, 0);
+            float4 c = i + 2 * stride < n16 ? src[i + 2 * stride] : make_float4(0, 0, 0, 0);
+            float4 d = i + 3 * stride < n16 ? src[i + 3 * stride] : make_float4(0, 0, 0, 0);
+            acc += (a.x + a.y + a.z + a.w) + (b.x + b.y + b.z + b.w) + (c.x + c.y + c.z + c.w) + (d.x + d.y + d.z + d.w);
+        }
+    }
+    if (acc == 12345.678f) *sink = acc;  // never true for the zero-filled buffer: keeps the loads alive
+}
+#endif
+
 }  // namespace
 }  // namespace lj
 
@@ -200,6 +206,7 @@ static int timed_done(cudaEvent_t e0, cudaEvent_t e1, double *kernel_ms) {
 
 extern "C" int lj_trace_closest(lj_scene *s, const lj_ray *rays, int64_t n, lj_hit *hits, double *kernel_ms) {
     LJ_CHECK_ARGS(s && rays && hits && n >= 0);
+    DeviceGuard guard(s->device);
     if (n == 0) return LJ_OK;
     DevBuf<lj_ray> dr(n); DevBuf<lj_hit> dh(n);
     LJ_CUDA(dr.err); LJ_CUDA(dh.err);
@@ -215,6 +222,7 @@ extern "C" int lj_trace_closest(lj_scene *s, const lj_ray *rays, int64_t n, lj_h
 
 extern "C" int lj_trace_any(lj_scene *s, const lj_ray *rays, int64_t n, uint8_t *occluded, double *kernel_ms) {
     LJ_CHECK_ARGS(s && rays && occluded && n >= 0);
+    DeviceGuard guard(s->device);
     if (n == 0) return LJ_OK;
     DevBuf<lj_ray> dr(n); DevBuf<uint8_t> dq(n);
     LJ_CUDA(dr.err); LJ_CUDA(dq.err);
@@ -230,6 +238,7 @@ extern "C" int lj_trace_any(lj_scene *s, const lj_ray *rays, int64_t n, uint8_t 
 
 extern "C" int lj_intersect(lj_scene *s, const lj_ray *rays, const float *rd, int64_t n, lj_vertex *vertices) {
     LJ_CHECK_ARGS(s && rays && vertices && n >= 0);
+    DeviceGuard guard(s->device);
     if (n == 0) return LJ_OK;
     DevBuf<lj_ray> dr(n); DevBuf<lj_vertex> dv(n); DevBuf<float> dd(rd ? 2 * n : 1);
     LJ_CUDA(dr.err); LJ_CUDA(dv.err); LJ_CUDA(dd.err);
@@ -244,6 +253,7 @@ extern "C" int lj_intersect(lj_scene *s, const lj_ray *rays, const float *rd, in
 
 extern "C" int lj_bsdf_batch(lj_scene *s, const lj_bsdf_query *q, int64_t n, lj_bsdf_result *out) {
     LJ_CHECK_ARGS(s && q && out && n >= 0);
+    DeviceGuard guard(s->device);
     if (n == 0) return LJ_OK;
     DevBuf<lj_bsdf_query> dq(n); DevBuf<lj_bsdf_result> dr(n);
     LJ_CUDA(dq.err); LJ_CUDA(dr.err);
@@ -257,6 +267,7 @@ extern "C" int lj_bsdf_batch(lj_scene *s, const lj_bsdf_query *q, int64_t n, lj_
 
 extern "C" int lj_medium_batch(lj_scene *s, const lj_medium_query *q, int64_t n, lj_medium_result *out) {
     LJ_CHECK_ARGS(s && q && out && n >= 0);
+    DeviceGuard guard(s->device);
     if (n == 0) return LJ_OK;
     for (int64_t i = 0; i < n; i++)
         if (q[i].medium_id < 0 || q[i].medium_id >= s->dev.num_media) { set_error("medium id out of range"); return LJ_ERR_INVALID; }
@@ -272,6 +283,7 @@ extern "C" int lj_medium_batch(lj_scene *s, const lj_medium_query *q, int64_t n,
 
 extern "C" int lj_light_batch(lj_scene *s, const lj_light_query *q, int64_t n, lj_light_result *out) {
     LJ_CHECK_ARGS(s && q && out && n >= 0);
+    DeviceGuard guard(s->device);
     if (s->dev.num_lights <= 0) { set_error("scene has no lights"); return LJ_ERR_INVALID; }
     if (n == 0) return LJ_OK;
     DevBuf<lj_light_query> dq(n); DevBuf<lj_light_result> dr(n);
@@ -286,6 +298,7 @@ extern "C" int lj_light_batch(lj_scene *s, const lj_light_query *q, int64_t n, l
 
 extern "C" int lj_camera_rays(lj_scene *s, const float *xy, int64_t n, lj_ray *rays) {
     LJ_CHECK_ARGS(s && xy && rays && n >= 0);
+    DeviceGuard guard(s->device);
     if (n == 0) return LJ_OK;
     DevBuf<float> dq(2 * n); DevBuf<lj_ray> dr(n);
     LJ_CUDA(dq.err); LJ_CUDA(dr.err);
@@ -299,6 +312,7 @@ extern "C" int lj_camera_rays(lj_scene *s, const float *xy, int64_t n, lj_ray *r
 
 extern "C" int lj_texture_batch(lj_scene *s, int32_t material_id, int32_t slot, const float *q, int64_t n, float *out_rgb) {
     LJ_CHECK_ARGS(s && q && out_rgb && n >= 0 && material_id >= 0 && material_id < s->dev.num_materials && slot >= 0 && slot < LJ_NUM_TEX_SLOTS);
+    DeviceGuard guard(s->device);
     if (n == 0) return LJ_OK;
     DevBuf<float> dq(3 * n), dr(3 * n);
     LJ_CUDA(dq.err); LJ_CUDA(dr.err);
@@ -328,4 +342,43 @@ extern "C" int lj_pcg32_batch(uint64_t first_stream, uint64_t seed, int32_t n_st
     if (out_u32) LJ_CUDA(du.down(out_u32, n));
     if (out_f32) LJ_CUDA(df.down(out_f32, n));
     return LJ_OK;
+}
+
+extern "C" int lj_measure_read_bandwidth(int64_t bytes, int32_t iters, double *gb_per_s) {
+    LJ_CHECK_ARGS(bytes >= 16 && iters > 0 && gb_per_s);
+#if defined(LJ_HOSTSIM)
+    set_error("no device in the host simulation");
+    return LJ_ERR_UNSUPPORTED;
+#else
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); set_error("no CUDA device"); return LJ_ERR_NO_DEVICE; }
+    LJ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const long long n16 = bytes / 16;
+    float4 *buf = nullptr;
+    float *sink = nullptr;
+    LJ_CUDA(cudaMalloc(&buf, (size_t)n16 * 16));
+    cudaError_t e = cudaMalloc(&sink, sizeof(float));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (e == cudaSuccess) e = cudaMemset(buf, 0, (size_t)n16 * 16);
+    if (e == cudaSuccess) e = cudaEventCreate(&e0);
+    if (e == cudaSuccess) e = cudaEventCreate(&e1);
+    float ms = 0;
+    if (e == cudaSuccess) {
+        const int grid = std::max(1, sms) * 8;
+        LJ_LAUNCH(k_read_stream, grid, 256, (cudaStream_t)0, buf, n16, 2, sink);  // warm-up: brings the set into L2 if it fits
+        cudaEventRecord(e0, 0);
+        LJ_LAUNCH(k_read_stream, grid, 256, (cudaStream_t)0, buf, n16, iters, sink);
+        cudaEventRecord(e1, 0);
+        e = cudaEventSynchronize(e1);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+    }
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    cudaFree(buf);
+    if (sink) cudaFree(sink);
+    if (e != cudaSuccess) return cuda_fail(e, "read-bandwidth probe");
+    *gb_per_s = (double)n16 * 16.0 * iters / (ms * 1e-3) / 1e9;
+    return LJ_OK;
+#endif
 }

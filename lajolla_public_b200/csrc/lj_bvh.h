@@ -183,19 +183,35 @@ struct Trav {
     uint32_t octinv4;
     U2 G, Gt;      // current node group / primitive group (y == 0: empty)
     int sp;
-    U2 stack[kStack8];
 };
+// Where the group stack of a traversal lives: in the thread's local memory (TravL, the per-thread loops and the
+// walk kernels), or in a per-warp scratch area addressed by ray (k_trace_q, wavefront.cu).
+struct LocalStack {
+    U2 e[kStack8];
+    LJ_HD void put(int k, U2 v) { e[k] = v; }
+    LJ_HD U2 get(int k) const { return e[k]; }
+};
+struct StridedStack {  // entry k of this ray at base[k * stride]
+    U2 *base;
+    int stride;
+    LJ_HD void put(int k, U2 v) { base[(size_t)k * stride] = v; }
+    LJ_HD U2 get(int k) const { return base[(size_t)k * stride]; }
+};
+struct TravL : Trav { LocalStack stack; };
 
 // Invariant between steps (kept by trav_next_group): G.y is either 0 or carries at least one hit bit, and the
 // stack is only non-empty while G or Gt is, so "finished" is simply both groups being empty.
 LJ_HD bool trav_done(const Trav &tr) { return (tr.G.y | tr.Gt.y) == 0; }
 
+LJ_HD V3 trav_idir(V3 d) {
+    const float tiny = 8.271806e-25f;  // 2^-80: keeps 2^e * idir finite for any node scale
+    return mk3(1.0f / (fabsf(d.x) > tiny ? d.x : copysignf(tiny, d.x)),
+               1.0f / (fabsf(d.y) > tiny ? d.y : copysignf(tiny, d.y)),
+               1.0f / (fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z)));
+}
 LJ_HD void trav_init(Trav &tr, V3 o, V3 d, float tnear, float tfar) {
     tr.o = o; tr.d = d;
-    const float tiny = 8.271806e-25f;  // 2^-80: keeps 2^e * idir finite for any node scale
-    tr.idir = mk3(1.0f / (fabsf(d.x) > tiny ? d.x : copysignf(tiny, d.x)),
-                  1.0f / (fabsf(d.y) > tiny ? d.y : copysignf(tiny, d.y)),
-                  1.0f / (fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z)));
+    tr.idir = trav_idir(d);
     tr.tnear = tnear;
     tr.hit.prim = kNoHit; tr.hit.t = tfar; tr.hit.u = tr.hit.v = 0;
     uint32_t oct = (d.x < 0 ? 1u : 0u) | (d.y < 0 ? 2u : 0u) | (d.z < 0 ? 4u : 0u);
@@ -209,11 +225,12 @@ LJ_HD void trav_init(Trav &tr, V3 o, V3 d, float tnear, float tfar) {
 
 // Pop the nearest unvisited child of node group tr.G, test its 8 children: the hit internal children
 // become the new tr.G (the rest of the old group is pushed), the hit leaf slots become tr.Gt.
-LJ_HD void trav_node(const DevNode8 *nodes, Trav &tr) {
+template <class Stack>
+LJ_HD void trav_node(const DevNode8 *nodes, Trav &tr, Stack &stack) {
     U2 G = tr.G;
     int bit = bfind32(G.y);
     G.y &= ~(1u << bit);
-    if (G.y & 0xff000000u) tr.stack[tr.sp++] = G;
+    if (G.y & 0xff000000u) stack.put(tr.sp++, G);
     uint32_t slot = ((uint32_t)(bit - 24) ^ (tr.octinv4 & 0xffu)) & 7u;
     uint32_t rel = (uint32_t)popc32(G.y & ~(0xffffffffu << slot) & 0xffu);
     const DevNode8 *nd = nodes + (G.x + rel);
@@ -294,9 +311,10 @@ LJ_HD bool trav_prim(const DevPrim *prims, Trav &tr) {
 
 // After a step: if both groups are used up, pop the next one.  A popped entry is either a node group or a
 // postponed primitive group (no hit bits in the top byte); the latter lands in tr.Gt.
-LJ_HD void trav_next_group(Trav &tr) {
+template <class Stack>
+LJ_HD void trav_next_group(Trav &tr, const Stack &stack) {
     if ((tr.G.y | tr.Gt.y) == 0 && tr.sp > 0) {
-        U2 e = tr.stack[--tr.sp];
+        U2 e = stack.get(--tr.sp);
         if (e.y & 0xff000000u) tr.G = e; else tr.Gt = e;
     }
 }
@@ -313,14 +331,14 @@ LJ_HD void trav_finish_closest(const DevPrim *prims, Trav &tr) {
 // Plain single-ray loop (query seam S2 and shading-side helpers).
 template <bool ANY>
 LJ_HD bool trace8(const DevNode8 *nodes, const DevPrim *prims, V3 o, V3 d, float tnear, float tfar, Hit &hit) {
-    Trav tr;
+    TravL tr;
     trav_init(tr, o, d, tnear, tfar);
     while (!trav_done(tr)) {
-        if (tr.Gt.y == 0) trav_node(nodes, tr);
+        if (tr.Gt.y == 0) trav_node(nodes, tr, tr.stack);
         while (tr.Gt.y != 0) {
             if (trav_prim<ANY>(prims, tr)) { trav_terminate(tr); break; }
         }
-        trav_next_group(tr);
+        trav_next_group(tr, tr.stack);
     }
     if (!ANY) trav_finish_closest(prims, tr);
     hit = tr.hit;

@@ -124,6 +124,7 @@ void *pool_block_take(int device, size_t bytes, size_t *got_bytes) {
         }
     }
     void *b = nullptr;
+    DeviceGuard guard(device);
     if (cudaMalloc(&b, bytes) != cudaSuccess) return nullptr;
     *got_bytes = bytes;
     return b;
@@ -135,7 +136,7 @@ void pool_block_give(int device, void *block, size_t bytes) {
         old = g_cached.block;
         g_cached = {device, block, bytes};
     }
-    if (old) cudaFree(old);
+    if (old) cudaFree(old);  // (cudaFree works on a pointer of any device)
 }
 }  // namespace lj
 
@@ -167,6 +168,7 @@ extern "C" int lj_init(int device) {
 
 extern "C" void lj_scene_destroy(lj_scene *s) {
     if (!s) return;
+    DeviceGuard guard(s->device);
     cudaDeviceSynchronize();  // the caller's streams may still read the tables
     for (void *p : s->allocations) lj_dev_free(p);
     if (s->pool_block) pool_block_give(s->device, s->pool_block, s->pool_bytes);
@@ -175,6 +177,7 @@ extern "C" void lj_scene_destroy(lj_scene *s) {
     for (cudaEvent_t e : s->event_pool) cudaEventDestroy(e);
     if (s->d_counters) cudaFree(s->d_counters);
     if (s->d_cursors) cudaFree(s->d_cursors);
+    if (s->d_qstack) cudaFree(s->d_qstack);
     if (s->h_counters) cudaFreeHost(s->h_counters);
     for (auto &e : s->ev) if (e) cudaEventDestroy(e);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -539,6 +542,7 @@ extern "C" int lj_scene_get_light_table(lj_scene *s, float *pmf, float *cdf) {
 extern "C" int lj_scene_get_mip_level(lj_scene *s, int32_t channels, int32_t image_id, int32_t level,
                                       int32_t *width, int32_t *height, float *data) {
     if (!s || image_id < 0 || image_id >= (int)s->h_images3.size()) { set_error("bad image id"); return LJ_ERR_INVALID; }
+    DeviceGuard guard(s->device);
     const DevImage &d = s->h_images3[image_id];
     if (d.channels != channels || level < 0 || level >= d.levels) { set_error("bad level/channels"); return LJ_ERR_INVALID; }
     if (width) *width = d.w[level];

@@ -9,6 +9,10 @@
 #include "bvh_build.cuh"
 #include "lj_path.h"
 
+namespace lj {
+struct LaunchGeom { int trace_blocks = 0, walk_blocks = 1, step_blocks = 1, flight_blocks = 1, q_blocks = 1; };
+}  // namespace lj
+
 struct lj_scene {
     lj::DevScene dev;                 // by-value kernel parameter
     std::vector<void *> allocations;  // everything cudaMalloc'ed for this scene
@@ -30,11 +34,43 @@ struct lj_scene {
     std::vector<cudaEvent_t> event_pool;
     unsigned long long *d_counters = nullptr, *h_counters = nullptr;
     unsigned int *d_cursors = nullptr;
+    lj::LaunchGeom geom;              // persistent grid sizes for this scene's device
+    void *d_qstack = nullptr;         // scratch group stacks of k_trace_q
+    int qdepth = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {};
 };
 
 namespace lj {
+// internal Hit (BVH leaf order) -> the ABI's lj_hit (shape id, primitive id, Embree-style (u, v))
+LJ_HD void hit_to_abi(const DevScene &sc, V3 org, V3 dir, const Hit &h, lj_hit &out) {
+    if (h.prim == kNoHit) { out.t = h.t; out.u = 0; out.v = 0; out.shape_id = -1; out.primitive_id = -1; return; }
+    V4 pc = ld4(&sc.prims[h.prim].c);
+    out.t = h.t;
+    out.shape_id = prim_shape_id(pc);
+    out.primitive_id = prim_primitive_id(pc);
+    if (prim_is_sphere(pc)) {
+        V4 pa = ld4(&sc.prims[h.prim].a);
+        V2 st = sphere_st((org + dir * h.t) - xyz(pa), pa.w);
+        out.u = st.x; out.v = st.y;
+    } else {
+        out.u = h.u; out.v = h.v;
+    }
+}
+
+// Makes the scene's device current on the calling thread for the lifetime of the guard (every entry point that
+// takes an lj_scene* holds one: streams, events and allocations of a scene belong to its device).
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != device) switched = cudaSetDevice(device) == cudaSuccess;
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard &) = delete;
+    DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
+
 // Path-pool blocks (0.6-0.9 GB) are recycled across scenes of one process: a cudaMalloc / cudaFree pair of that size
 // stalls the host for up to 100 ms now and then, which a render-per-scene caller pays on every call.
 void *pool_block_take(int device, size_t bytes, size_t *got_bytes);

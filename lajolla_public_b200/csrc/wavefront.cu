@@ -22,7 +22,7 @@
 
 namespace lj {
 
-enum { C_SAMPLES = 0, C_CLOSEST, C_SHADOW, C_BOUNCES, C_ACTIVE, C_NEXT, C_NODE_STEPS, C_PRIM_TESTS, C_COUNT };
+enum { C_SAMPLES = 0, C_CLOSEST, C_SHADOW, C_BOUNCES, C_ACTIVE, C_NEXT, C_NODE_STEPS, C_PRIM_TESTS, C_NODE_PASSES, C_PRIM_PASSES, C_COUNT };
 // Statistics counters every warp of a full-pool kernel adds to are striped over kStripes addresses (folded on the
 // host): 131k same-address reductions per launch serialise in one L2 slice otherwise.
 constexpr int kStripes = 64;
@@ -42,6 +42,12 @@ struct WaveArgs {
     int chunk, shadow_chunk;               // slots a warp takes from the cursor at a time
     int track_refill;                      // k_flight / walk: refill once fewer lanes than this are tracking
     int trav_min;                          // k_trace<3>: lanes that must wait to traverse before a traversal pass pre-empts tracking
+    // k_trace_q: per-warp scratch stacks (qdepth entries x kQRays rays x 8 B per warp) and its refill threshold
+    U2 *qstack;
+    int qdepth, q_refill, q_chunk;
+    // image-space split (lj_render_opts.split == LJ_SPLIT_TILES): this call renders the 8x4 pixel tiles t with
+    // t % tile_stride == tile_offset; a sample split leaves tile_stride = 1
+    int tile_stride, tile_offset, tiles_local;
 };
 
 __device__ __forceinline__ void warp_add(unsigned long long *ctr, unsigned v) {
@@ -109,10 +115,10 @@ __global__ void __launch_bounds__(256) k_regen(const LJ_GRID_CONSTANT DevScene s
         bool ok = k < a.total_items;
         uint32_t x = 0, y = 0, sample = 0;
         if (ok) {
-            unsigned long long per_sample = (unsigned long long)a.tiles_x * a.tiles_y * 32ull;
+            unsigned long long per_sample = (unsigned long long)a.tiles_local * 32ull;
             sample = a.rp.sample_begin + (uint32_t)(k / per_sample);
             uint32_t p = (uint32_t)(k % per_sample);
-            uint32_t tile = p >> 5, l = p & 31;
+            uint32_t tile = (p >> 5) * (uint32_t)a.tile_stride + (uint32_t)a.tile_offset, l = p & 31;
             x = (tile % a.tiles_x) * 8 + (l & 7);
             y = (tile / a.tiles_x) * 4 + (l >> 3);
             ok = x < (uint32_t)a.rp.width && y < (uint32_t)a.rp.height;
@@ -176,7 +182,7 @@ __global__ void __launch_bounds__(128, MODE >= 2 ? LJ_WALK_MIN_BLOCKS : (MODE ==
     const unsigned n = (unsigned)a.pool.capacity;
     unsigned int *cursor = &a.cursors[MODE == 0 ? 0 : 1];
     const int lane = LJ_LANE();
-    Trav tr;
+    TravL tr;
     trav_terminate(tr);
     int slot = -1;
     bool has_ray = false;
@@ -185,7 +191,7 @@ __global__ void __launch_bounds__(128, MODE >= 2 ? LJ_WALK_MIN_BLOCKS : (MODE ==
     unsigned chunk_next = 0, chunk_end = 0;
     unsigned cur_mask = 0, cur_word = 0;  // MODE >= 1: unread bits of the warp's current sh_mask word
     const unsigned chunk = (unsigned)(MODE == 1 ? a.shadow_chunk : a.chunk);  // walks: small runs, their cost per slot varies a lot
-    unsigned traced = 0, node_steps = 0, prim_tests = 0;
+    unsigned traced = 0, node_steps = 0, prim_tests = 0, node_passes = 0, prim_passes = 0;
     for (;;) {
         // ---- fetch: lanes without a ray take the next slots.  The warp owns a private run of slots [chunk_next,
         // chunk_end) and goes to the global cursor only when that runs out: one same-address atomic per a.chunk
@@ -299,23 +305,24 @@ __global__ void __launch_bounds__(128, MODE >= 2 ? LJ_WALK_MIN_BLOCKS : (MODE ==
             if (wm && trav_phase) {
                 const unsigned pm = __ballot_sync(0xffffffffu, has_p);
                 if (__popc(pm) >= a.prim_min_lanes || pm == wm) {
+                    if (lane == 0) prim_passes++;
                     if (has_p) {
                         prim_tests++;
                         if (trav_prim<SHADOW>(sc.prims, tr)) trav_terminate(tr);  // any-hit ends at the first hit
                     }
-                } else if (work) {
+                } else if ((lane == 0 ? (void)node_passes++ : (void)0), work) {
                     bool descend = !has_p;
                     if (has_p && tr.G.y != 0 && tr.sp < kTriPostponeMax) {
-                        tr.stack[tr.sp++] = tr.Gt;  // postpone these primitives, keep descending
+                        tr.stack.put(tr.sp++, tr.Gt);  // postpone these primitives, keep descending
                         tr.Gt.y = 0;
                         descend = true;
                     }
                     if (descend) {
                         node_steps++;
-                        trav_node(sc.nodes8, tr);
+                        trav_node(sc.nodes8, tr, tr.stack);
                     }
                 }
-                trav_next_group(tr);
+                trav_next_group(tr, tr.stack);
             }
             if (STEP && !trav_phase) {
                 // A lane that finished traversing its segment starts tracking over it (or goes straight to the surface
@@ -386,7 +393,233 @@ __global__ void __launch_bounds__(128, MODE >= 2 ? LJ_WALK_MIN_BLOCKS : (MODE ==
     warp_add(&a.counters[MODE == 0 ? C_CLOSEST : C_SHADOW], traced);
     warp_add(&a.counters[C_NODE_STEPS], node_steps);
     warp_add(&a.counters[C_PRIM_TESTS], prim_tests);
+    warp_add(&a.counters[C_NODE_PASSES], node_passes);
+    warp_add(&a.counters[C_PRIM_PASSES], prim_passes);
 }
+
+// K2 / K3, queue form (the kernels lj_render launches for the path integrator).  k_trace above runs one ray per
+// lane and votes per pass for a node step or a primitive step; measured on sponza only 18 of 32 lanes do the voted
+// step (profiles/r01w_sponza_ncu.txt) -- the others hold a ray that wants the other kind of step, or none.  Here a
+// warp owns kQRays = 64 ray slots whose traversal state lives in SHARED memory (structure of arrays, 4.2 KB per warp),
+// and every pass compacts the slots that want the chosen kind of step onto the lanes with two ballots and a rank
+// (the shared-memory / warp-ballot compaction north_star asks for): a pass runs with 32 active lanes whenever 32 of
+// the 64 rays want the same step.  Three kinds of step: NODE (one wide-node test), PRIM (one primitive test), FIN
+// (write the result of a finished ray: barycentrics + fp64 t for closest hits, the NEE contribution for shadow
+// rays).  Group stacks sit in a per-warp global scratch area addressed [entry][ray] (same cache path as local
+// memory, but reachable from whichever lane processes the ray).  Same results as trace8 / k_trace: the step
+// functions are the same (lj_bvh.h) and the equal-t tie policy makes the winner independent of visiting order.
+constexpr int kQWarps = 4;
+constexpr int kQRays = 2 * LJ_WARP_WIDTH;
+enum { Q_EMPTY = 0, Q_NODE = 1, Q_PRIM = 2, Q_FIN = 3 };
+
+struct QRays {
+    float ox[kQRays], oy[kQRays], oz[kQRays], dx[kQRays], dy[kQRays], dz[kQRays], tnear[kQRays], tfar[kQRays];
+    int prim[kQRays], slot[kQRays];
+    uint32_t Gx[kQRays], Gy[kQRays], Tx[kQRays], Ty[kQRays], sp[kQRays], status[kQRays];
+    uint32_t list[LJ_WARP_WIDTH];
+};
+
+LJ_HD uint32_t q_status_of(const Trav &tr) { return tr.Gt.y ? (uint32_t)Q_PRIM : (tr.G.y ? (uint32_t)Q_NODE : (uint32_t)Q_FIN); }
+
+// a new ray into slot r of the warp's table
+LJ_HD void q_put_ray(QRays &q, int r, int slot, V3 o, V3 d, float tnear, float tfar) {
+    q.ox[r] = o.x; q.oy[r] = o.y; q.oz[r] = o.z; q.dx[r] = d.x; q.dy[r] = d.y; q.dz[r] = d.z;
+    q.tnear[r] = tnear; q.tfar[r] = tfar;
+    q.prim[r] = kNoHit; q.slot[r] = slot;
+    q.Gx[r] = 0; q.Gy[r] = (tnear <= tfar) ? 0x80000000u : 0u;  // root group, as trav_init
+    q.Tx[r] = 0; q.Ty[r] = 0; q.sp[r] = 0;
+    q.status[r] = (tnear <= tfar) ? (uint32_t)Q_NODE : (uint32_t)Q_FIN;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kQWarps * LJ_WARP_WIDTH, 8) k_trace_q(const LJ_GRID_CONSTANT DevScene sc, const LJ_GRID_CONSTANT WaveArgs a) {
+    constexpr bool SHADOW = MODE == 1;
+    constexpr int W = LJ_WARP_WIDTH;
+    __shared__ QRays s_rays[kQWarps];
+    const int lane = LJ_LANE();
+#if defined(LJ_HOSTSIM)
+    const int warp = 0;
+    const size_t warp_global = 0;
+#else
+    const int warp = (int)(threadIdx.x / W);
+    const size_t warp_global = (size_t)blockIdx.x * kQWarps + warp;
+#endif
+    QRays &q = s_rays[warp];
+    U2 *const stack_base = a.qstack + warp_global * (size_t)a.qdepth * kQRays;
+    const unsigned n = (unsigned)a.pool.capacity;
+    unsigned int *cursor = &a.cursors[MODE];
+    const unsigned chunk = (unsigned)a.q_chunk;
+    const unsigned lt = (1u << lane) - 1u;
+    unsigned chunk_next = 0, chunk_end = 0;   // MODE 0: slots; MODE 1: sh_mask words
+    unsigned cur_mask = 0, cur_word = 0;
+    bool drained = false, global_out = false;
+    unsigned traced = 0, node_steps = 0, prim_tests = 0, node_passes = 0, prim_passes = 0;
+    q.status[lane] = Q_EMPTY;
+    q.status[lane + W] = Q_EMPTY;
+    __syncwarp();
+    for (unsigned pass = 0;; pass++) {
+        uint32_t s0 = q.status[lane], s1 = q.status[lane + W];
+        const unsigned mN0 = __ballot_sync(0xffffffffu, s0 == Q_NODE), mN1 = __ballot_sync(0xffffffffu, s1 == Q_NODE);
+        const unsigned mP0 = __ballot_sync(0xffffffffu, s0 == Q_PRIM), mP1 = __ballot_sync(0xffffffffu, s1 == Q_PRIM);
+        const unsigned mF0 = __ballot_sync(0xffffffffu, s0 == Q_FIN), mF1 = __ballot_sync(0xffffffffu, s1 == Q_FIN);
+        const int cN = __popc(mN0) + __popc(mN1), cP = __popc(mP0) + __popc(mP1), cF = __popc(mF0) + __popc(mF1);
+        const int live = cN + cP;
+        const bool want_refill = !drained && live < a.q_refill;
+        int kind;
+        if (cF >= W || (cF > 0 && (want_refill || live == 0))) {
+            kind = Q_FIN;
+        } else if (want_refill) {
+            // ---- fetch new rays into the empty slots (both halves of the table), from the warp's private run of the
+            // pool and, when that runs out, the global cursor: one same-address atomic per q_chunk slots
+            if (MODE == 0) {
+                const unsigned e0 = __ballot_sync(0xffffffffu, s0 == Q_EMPTY), e1 = __ballot_sync(0xffffffffu, s1 == Q_EMPTY);
+                const unsigned c0 = (unsigned)__popc(e0), cnt = c0 + (unsigned)__popc(e1);
+                const unsigned lim = chunk_end < n ? chunk_end : n;
+                const unsigned left = chunk_next < lim ? lim - chunk_next : 0u;
+                unsigned nb = 0;
+                bool fresh = false;
+                if (cnt > left && !global_out) {
+                    if (lane == 0) nb = atomicAdd(cursor, chunk);
+                    nb = __shfl_sync(0xffffffffu, nb, 0);
+                    if (nb >= n) global_out = true; else fresh = true;
+                }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                for (int half = 0; half < 2; half++) {
+                    const bool mine = (half ? s1 : s0) == Q_EMPTY;
+                    const unsigned rank = half ? c0 + (unsigned)__popc(e1 & lt) : (unsigned)__popc(e0 & lt);
+                    const unsigned idx = rank < left ? chunk_next + rank : (fresh ? nb + (rank - left) : 0xffffffffu);
+                    if (mine && idx < n && (f2u(a.pool.meta[idx].y) & kAlive)) {
+                        V4 o = a.pool.ray_o[idx], d = a.pool.ray_d[idx];
+                        q_put_ray(q, lane + half * W, (int)idx, xyz(o), xyz(d), o.w, d.w);
+                        traced++;
+                    }
+                }
+                if (fresh) { chunk_next = nb + (cnt - left); chunk_end = nb + chunk; }
+                else chunk_next += cnt < left ? cnt : left;
+                drained = global_out && chunk_next >= (chunk_end < n ? chunk_end : n);
+            } else {
+                // shadow rays exist for a fraction of the slots: hand out the set bits of pool.sh_mask (one word per
+                // warp of the shade kernel), so no record of a slot without a ray is ever loaded
+                while (!drained) {
+                    const unsigned e0 = __ballot_sync(0xffffffffu, s0 == Q_EMPTY), e1 = __ballot_sync(0xffffffffu, s1 == Q_EMPTY);
+                    const unsigned c0 = (unsigned)__popc(e0), cnt = c0 + (unsigned)__popc(e1);
+                    if (!cnt) break;
+                    if (cur_mask == 0) {
+                        if (chunk_next >= chunk_end) {
+                            unsigned nb = 0;
+                            if (lane == 0) nb = atomicAdd(cursor, chunk);
+                            nb = __shfl_sync(0xffffffffu, nb, 0);
+                            if (nb >= n) { drained = true; break; }
+                            chunk_next = nb / W;
+                            chunk_end = ((nb + chunk < n ? nb + chunk : n) + W - 1) / W;
+                        }
+                        cur_word = chunk_next++;
+                        cur_mask = a.pool.sh_mask[cur_word];
+                        continue;
+                    }
+                    const unsigned avail = (unsigned)__popc(cur_mask), take = cnt < avail ? cnt : avail;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                    for (int half = 0; half < 2; half++) {
+                        const bool mine = (half ? s1 : s0) == Q_EMPTY;
+                        const unsigned rank = half ? c0 + (unsigned)__popc(e1 & lt) : (unsigned)__popc(e0 & lt);
+                        if (mine && rank < take) {
+                            const int slot = (int)(cur_word * W + __fns(cur_mask, 0, (int)rank + 1));
+                            V4 sd = a.pool.sh_d[slot];
+                            // the segment starts at the shaded vertex: pool.ray_o if the path continued; if it ended,
+                            // ray_o still holds the previous origin and the vertex is rebuilt from the old ray
+                            V3 org = xyz(a.pool.ray_o[slot]);
+                            if (!(f2u(a.pool.meta[slot].y) & kAlive)) org = org + xyz(a.pool.ray_d[slot]) * a.pool.hit[slot].x;
+                            q_put_ray(q, lane + half * W, slot, org, xyz(sd), sc.shadow_eps, sd.w);
+                            if (half) s1 = Q_NODE; else s0 = Q_NODE;  // (any non-empty value: only emptiness is re-read here)
+                            traced++;
+                        }
+                    }
+                    const unsigned last = __fns(cur_mask, 0, (int)take);  // position of the last bit handed out
+                    cur_mask &= ~((2u << last) - 1u);
+                    if (take == cnt) break;
+                }
+            }
+            __syncwarp();
+            continue;
+        } else if (live == 0) {
+            break;  // pool exhausted, nothing in flight, nothing left to write
+        } else {
+            // the kind that fills more lanes; primitives first on a tie (they shorten the ray)
+            const int fN = cN < W ? cN : W, fP = cP < W ? cP : W;
+            kind = fP >= fN ? Q_PRIM : Q_NODE;
+        }
+        // ---- compaction: the first W slots that want this kind of step, the two halves taking turns to go first
+        {
+            const unsigned m0 = kind == Q_NODE ? mN0 : (kind == Q_PRIM ? mP0 : mF0);
+            const unsigned m1 = kind == Q_NODE ? mN1 : (kind == Q_PRIM ? mP1 : mF1);
+            const bool flip = (pass & 1u) != 0;
+            const unsigned first = flip ? m1 : m0, second = flip ? m0 : m1;
+            const int cf = __popc(first);
+            if ((first >> lane) & 1u) { int r = __popc(first & lt); if (r < W) q.list[r] = (uint32_t)(lane + (flip ? W : 0)); }
+            if ((second >> lane) & 1u) { int r = cf + __popc(second & lt); if (r < W) q.list[r] = (uint32_t)(lane + (flip ? 0 : W)); }
+            __syncwarp();
+            const int nsel = cf + __popc(second) < W ? cf + __popc(second) : W;
+            if (lane == 0) { if (kind == Q_NODE) node_passes++; else if (kind == Q_PRIM) prim_passes++; }
+            if (lane < nsel) {
+                const int r = (int)q.list[lane];
+                Trav tr;
+                tr.o = mk3(q.ox[r], q.oy[r], q.oz[r]);
+                tr.d = mk3(q.dx[r], q.dy[r], q.dz[r]);
+                tr.hit.t = q.tfar[r];
+                tr.hit.prim = q.prim[r];
+                tr.hit.u = tr.hit.v = 0;
+                if (kind == Q_FIN) {
+                    const int slot = q.slot[r];
+                    if (SHADOW) {
+                        if (tr.hit.prim == kNoHit) {
+                            V4 rd = a.pool.rad[slot], c = a.pool.sh_c[slot];
+                            a.pool.rad[slot] = mk4(rd.x + c.x, rd.y + c.y, rd.z + c.z, rd.w);
+                        }
+                    } else {
+                        trav_finish_closest(sc.prims, tr);
+                        a.pool.hit[slot] = mk4(tr.hit.t, tr.hit.u, tr.hit.v, u2f((uint32_t)tr.hit.prim));
+                    }
+                    q.status[r] = Q_EMPTY;
+                } else {
+                    tr.tnear = q.tnear[r];
+                    tr.G.x = q.Gx[r]; tr.G.y = q.Gy[r];
+                    tr.sp = (int)q.sp[r];
+                    StridedStack stk;
+                    stk.base = stack_base + r;
+                    stk.stride = kQRays;
+                    if (kind == Q_NODE) {
+                        tr.idir = trav_idir(tr.d);
+                        const uint32_t oct = (tr.d.x < 0 ? 1u : 0u) | (tr.d.y < 0 ? 2u : 0u) | (tr.d.z < 0 ? 4u : 0u);
+                        tr.octinv4 = (7u ^ oct) * 0x01010101u;
+                        node_steps++;
+                        trav_node(sc.nodes8, tr, stk);
+                    } else {
+                        tr.Gt.x = q.Tx[r]; tr.Gt.y = q.Ty[r];
+                        prim_tests++;
+                        if (trav_prim<SHADOW>(sc.prims, tr)) trav_terminate(tr);  // any-hit ends at the first hit
+                        q.tfar[r] = tr.hit.t;
+                        q.prim[r] = tr.hit.prim;
+                    }
+                    trav_next_group(tr, stk);
+                    q.Gx[r] = tr.G.x; q.Gy[r] = tr.G.y; q.Tx[r] = tr.Gt.x; q.Ty[r] = tr.Gt.y;
+                    q.sp[r] = (uint32_t)tr.sp;
+                    q.status[r] = q_status_of(tr);
+                }
+            }
+            __syncwarp();
+        }
+    }
+    warp_add(&a.counters[MODE == 0 ? C_CLOSEST : C_SHADOW], traced);
+    warp_add(&a.counters[C_NODE_STEPS], node_steps);
+    warp_add(&a.counters[C_PRIM_TESTS], prim_tests);
+    warp_add(&a.counters[C_NODE_PASSES], node_passes);
+    warp_add(&a.counters[C_PRIM_PASSES], prim_passes);
+}
+
 
 // K4
 template <int MIN_BLOCKS, bool CALLS>
@@ -399,24 +632,12 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_shade(const LJ_GRID_CONSTAN
         if (flags & kAlive) {
             PathState s;
             load_state(a.pool, i, s);
-#if defined(LJ_HOSTSIM)  // test-build tracing of one pixel's paths (LJ_DBG_PIXEL=y*w+x)
-            static const char *dbg = getenv("LJ_DBG_PIXEL");
-            const bool trace = dbg && (uint32_t)atoi(dbg) == s.pixel;
-            V3 T0 = s.T, L0 = s.L, o0 = s.o, d0 = s.d;
-#endif
             shade_path<CALLS>(sc, a.rp, s, cnt);
-#if defined(LJ_HOSTSIM)
-            if (trace) fprintf(stderr, "RAY %.9g %.9g %.9g %.9g %.9g %.9g OUT %.9g %.9g %.9g\n", o0.x, o0.y, o0.z, d0.x, d0.y, d0.z, s.d.x, s.d.y, s.d.z);
-            if (trace)
-                fprintf(stderr, "px %u smp %u nv %u prim %d t %g | T %g %g %g -> %g %g %g pdf %g | L %g -> %g | sh %g c %g %g %g | alive %d\n", s.pixel, s.sample,
-                        s.nv, s.hit.prim, s.hit.t, T0.x, T0.y, T0.z, s.T.x, s.T.y, s.T.z, s.pdf_sa, L0.x, s.L.x, s.sh_tfar, s.sh_c.x, s.sh_c.y, s.sh_c.z,
-                        (s.flags & kAlive) != 0);
-#endif
             store_state(a.pool, i, s, (s.flags & kAlive) != 0);
             has_shadow = s.sh_tfar >= 0;
         }
     }
-    {   // capacity is a multiple of the block size: whole warps are in range
+    {   // capacity is a multiple of 256 (render_impl): whole warps are in range
         unsigned m = __ballot_sync(0xffffffffu, has_shadow);
         if (LJ_LANE() == 0 && i < a.pool.capacity) a.pool.sh_mask[i / LJ_WARP_WIDTH] = m;
     }
@@ -594,7 +815,7 @@ static int ensure_pool(lj_scene *s, int capacity, bool vol) {
     if (s->pool_capacity == capacity && s->pool_block && (s->pool.vol0 != nullptr) == vol) return LJ_OK;
     if (s->pool_block) { pool_block_give(s->device, s->pool_block, s->pool_bytes); s->pool_block = nullptr; }
     const int kFields = vol ? 14 : 9;
-    s->pool_block = pool_block_take(s->device, (size_t)capacity * sizeof(V4) * kFields + (size_t)capacity / LJ_WARP_WIDTH * sizeof(uint32_t), &s->pool_bytes);
+    s->pool_block = pool_block_take(s->device, (size_t)capacity * sizeof(V4) * kFields + ((size_t)capacity + LJ_WARP_WIDTH - 1) / LJ_WARP_WIDTH * sizeof(uint32_t), &s->pool_bytes);
     if (!s->pool_block) { s->pool_capacity = 0; return cuda_fail(cudaErrorMemoryAllocation, "path pool allocation"); }
     V4 *base = (V4 *)s->pool_block;
     PathPool &p = s->pool;
@@ -622,6 +843,112 @@ struct EventPool {  // hands out the scene's events in order; they live until lj
     }
 };
 
+// Tuning overrides, read from the environment ONCE per process (first render); the defaults are the measured
+// optimum on sponza / hetvol (profiles/).  LJ_TRACE_KERNEL=0 selects the one-ray-per-lane k_trace<0|1> instead of
+// k_trace_q for the path integrator (A/B runs and the parity tests that compare the two).
+struct Tuning {
+    int prim_min_lanes = kPrimMinLanes, refill = kRefillThreshold, track_refill = 24, shadow_chunk = 128, trav_min = 4, chunk = 64;
+    int trace_kernel = 1, q_refill = 48, q_chunk = 128;
+    bool host_prof = false;
+};
+static const Tuning &tuning() {
+    static const Tuning t = [] {
+        Tuning v;
+        auto geti = [](const char *name, int &dst, int lo, int hi) {
+            if (const char *e = getenv(name)) dst = std::min(hi, std::max(lo, atoi(e)));
+        };
+        geti("LJ_PRIM_MIN_LANES", v.prim_min_lanes, 0, 32);
+        geti("LJ_REFILL", v.refill, 0, 32);
+        geti("LJ_TRACK_REFILL", v.track_refill, 0, 32);
+        geti("LJ_SHADOW_CHUNK", v.shadow_chunk, 32, 1 << 16);
+        geti("LJ_TRAV_MIN", v.trav_min, 1, 32);
+        geti("LJ_CHUNK", v.chunk, 32, 1 << 16);
+        geti("LJ_TRACE_KERNEL", v.trace_kernel, 0, 1);
+        geti("LJ_Q_REFILL", v.q_refill, 1, kQRays);
+        geti("LJ_Q_CHUNK", v.q_chunk, kQRays, 1 << 16);
+        v.host_prof = getenv("LJ_PROFILE_HOST") != nullptr;
+        return v;
+    }();
+    return t;
+}
+
+// Persistent grids: exactly one wave of resident CTAs (SM count x the occupancy of each kernel), per device.
+static int ensure_launch_geometry(lj_scene *s) {
+    LaunchGeom &g = s->geom;
+    if (g.trace_blocks > 0) return LJ_OK;
+#if defined(LJ_HOSTSIM)
+    g.trace_blocks = g.walk_blocks = g.step_blocks = g.flight_blocks = g.q_blocks = 1;
+#else
+    int sms = 0, a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, q0 = 0, q1 = 0;
+    LJ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
+    // k_trace_q keeps its ray tables in shared memory: ask for the largest carve-out so 8 CTAs stay resident
+    cudaFuncSetAttribute(k_trace_q<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_trace_q<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    LJ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a0, k_trace<0>, 128, 0));
+    LJ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a1, k_trace<1>, 128, 0));
+    LJ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a2, k_trace<2>, 128, 0));
+    LJ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a4, k_trace<3>, 128, 0));
+    LJ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a3, k_flight, 128, 0));
+    LJ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q0, k_trace_q<0>, kQWarps * LJ_WARP_WIDTH, 0));
+    LJ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q1, k_trace_q<1>, kQWarps * LJ_WARP_WIDTH, 0));
+    sms = std::max(1, sms);
+    g.trace_blocks = sms * std::max(1, std::min(a0, a1));
+    g.walk_blocks = sms * std::max(1, a2);
+    g.step_blocks = sms * std::max(1, a4);
+    g.flight_blocks = sms * std::max(1, a3);
+    g.q_blocks = sms * std::max(1, std::min(q0, q1));
+#endif
+    return LJ_OK;
+}
+
+// scratch stacks of k_trace_q: (tree depth + 2) entries x kQRays rays x 8 B per warp of the persistent grid
+static int ensure_qstack(lj_scene *s) {
+    int r = ensure_launch_geometry(s);
+    if (r != LJ_OK) return r;
+    if (s->d_qstack) return LJ_OK;
+    s->qdepth = std::max(4, s->info.bvh_depth + 2);
+    size_t bytes = (size_t)s->geom.q_blocks * kQWarps * s->qdepth * kQRays * sizeof(U2);
+    LJ_CUDA(cudaMalloc(&s->d_qstack, bytes));
+    return LJ_OK;
+}
+
+static void fill_trace_args(lj_scene *s, WaveArgs &a) {
+    const Tuning &t = tuning();
+    a.prim_min_lanes = t.prim_min_lanes;
+    a.refill_threshold = t.refill;
+    a.track_refill = t.track_refill;
+    a.shadow_chunk = t.shadow_chunk;
+    a.trav_min = t.trav_min;
+    a.chunk = t.chunk;
+    a.q_refill = std::min(t.q_refill, kQRays);  // (the host simulation has 2 ray slots per "warp")
+    a.q_chunk = t.q_chunk;
+    a.qstack = (U2 *)s->d_qstack;
+    a.qdepth = s->qdepth;
+    a.cursors = s->d_cursors;
+    a.counters = s->d_counters;
+}
+
+// closest-hit / shadow stage of one wave of the path integrator, as lj_render launches it
+static void launch_trace(lj_scene *s, const WaveArgs &a, int mode, cudaStream_t stream) {
+    const DevScene &sc = s->dev;
+    if (tuning().trace_kernel == 1) {
+        if (mode == 0) LJ_LAUNCH(k_trace_q<0>, s->geom.q_blocks, kQWarps * LJ_WARP_WIDTH, stream, sc, a);
+        else LJ_LAUNCH(k_trace_q<1>, s->geom.q_blocks, kQWarps * LJ_WARP_WIDTH, stream, sc, a);
+    } else {
+        if (mode == 0) LJ_LAUNCH(k_trace<0>, s->geom.trace_blocks, 128, stream, sc, a);
+        else LJ_LAUNCH(k_trace<1>, s->geom.trace_blocks, 128, stream, sc, a);
+    }
+}
+
+static int ensure_render_buffers(lj_scene *s, int npix, bool want_sq) {
+    if (!s->d_film) LJ_CUDA(cudaMalloc(&s->d_film, (size_t)npix * 16));
+    if (want_sq && !s->d_film_sq) LJ_CUDA(cudaMalloc(&s->d_film_sq, (size_t)npix * 16));
+    if (!s->d_counters) LJ_CUDA(cudaMalloc(&s->d_counters, sizeof(unsigned long long) * C_TOTAL));
+    if (!s->h_counters) LJ_CUDA(cudaMallocHost(&s->h_counters, sizeof(unsigned long long) * (C_TOTAL + 8)));
+    if (!s->d_cursors) LJ_CUDA(cudaMalloc(&s->d_cursors, 4 * sizeof(unsigned int)));
+    return ensure_qstack(s);
+}
+
 static int render_impl(lj_scene *s, const lj_render_opts *opts_in, float *d_out, float *d_var, cudaStream_t stream, lj_stats *stats) {
     lj_render_opts opts;
     memset(&opts, 0, sizeof(opts));
@@ -648,28 +975,34 @@ static int render_impl(lj_scene *s, const lj_render_opts *opts_in, float *d_out,
     int sb = opts.sample_begin, se = opts.sample_end;
     if (sb == 0 && se == 0) se = spp;
     if (sb < 0 || se > spp || sb >= se) { set_error("bad sample range"); return LJ_ERR_INVALID; }
+    if (opts.pool_paths < 0) { set_error("pool_paths < 0"); return LJ_ERR_INVALID; }
+    const int tile_stride = opts.tile_stride > 0 ? opts.tile_stride : 1;
+    if (opts.tile_offset < 0 || opts.tile_offset >= tile_stride) { set_error("bad tile split"); return LJ_ERR_INVALID; }
     int w = sc.camera.width, h = sc.camera.height, npix = w * h;
-    int capacity = opts.pool_paths > 0 ? opts.pool_paths : (1 << 22);
-    {
-        // no point in holding more slots than there are samples
-        unsigned long long want = (unsigned long long)npix * (unsigned)(se - sb);
-        if (want < (unsigned long long)capacity) capacity = (int)((want + 255) / 256 * 256);
-    }
-    const bool host_prof = getenv("LJ_PROFILE_HOST") != nullptr;  // host-side phase times on stderr
+    const int tiles_x = (w + 7) / 8, tiles_y = (h + 3) / 4, tiles = tiles_x * tiles_y;
+    const int tiles_local = tiles > opts.tile_offset ? (tiles - opts.tile_offset + tile_stride - 1) / tile_stride : 0;
+    const unsigned long long total_items = (unsigned long long)tiles_local * 32ull * (unsigned)(se - sb);
+    // Pool capacity: a multiple of 256 slots (whole blocks of k_regen, whole warps and sh_mask words everywhere), at
+    // least 1024, and no more slots than there are samples to start.  The default is sized to the work: 4 Mi slots for
+    // a full-size render, fewer when the call renders a small share (a rank of a strong-scaling run, a small image),
+    // so that short renders do not pay for clearing and sweeping an almost empty pool.
+    long long capacity = opts.pool_paths > 0 ? opts.pool_paths : (1 << 22);
+    if ((unsigned long long)capacity > total_items) capacity = (long long)total_items;
+    capacity = std::max<long long>(1024, (capacity + 255) / 256 * 256);
+    const Tuning &tune = tuning();
+    const bool host_prof = tune.host_prof;  // host-side phase times on stderr
     auto hp_t0 = std::chrono::steady_clock::now();
-    int r = ensure_pool(s, capacity, vol);
+    int r = ensure_pool(s, (int)capacity, vol);
     if (r != LJ_OK) return r;
-    if (!s->d_film) LJ_CUDA(cudaMalloc(&s->d_film, (size_t)npix * 16));
-    if (d_var && !s->d_film_sq) LJ_CUDA(cudaMalloc(&s->d_film_sq, (size_t)npix * 16));
-    if (!s->d_counters) LJ_CUDA(cudaMalloc(&s->d_counters, sizeof(unsigned long long) * C_TOTAL));
-    if (!s->h_counters) LJ_CUDA(cudaMallocHost(&s->h_counters, sizeof(unsigned long long) * (C_TOTAL + 8)));
-    if (!s->d_cursors) LJ_CUDA(cudaMalloc(&s->d_cursors, 4 * sizeof(unsigned int)));
+    r = ensure_render_buffers(s, npix, d_var != nullptr);
+    if (r != LJ_OK) return r;
     auto hp_t1 = std::chrono::steady_clock::now();
     unsigned long long *d_counters = s->d_counters;
     unsigned long long *h_counters = s->h_counters;  // C_COUNT final counters, then the ring of per-wave live-path counts
     unsigned long long *h_active = h_counters + C_TOTAL;
 
     WaveArgs a;
+    memset(&a, 0, sizeof(a));
     a.pool = s->pool;
     a.rp.spp_total = (uint32_t)spp;
     a.rp.sample_begin = (uint32_t)sb;
@@ -677,49 +1010,20 @@ static int render_impl(lj_scene *s, const lj_render_opts *opts_in, float *d_out,
     a.rp.seed = opts.seed ? opts.seed : kPcgDefaultSeed;
     a.rp.width = w;
     a.rp.height = h;
-    a.counters = d_counters;
     a.film = s->d_film;
     a.film_sq = d_var ? s->d_film_sq : nullptr;
-    a.tiles_x = (w + 7) / 8;
-    a.tiles_y = (h + 3) / 4;
-    a.total_items = (unsigned long long)a.tiles_x * a.tiles_y * 32ull * (unsigned)(se - sb);
-    a.prim_min_lanes = kPrimMinLanes;
-    a.refill_threshold = kRefillThreshold;
-    if (const char *e = getenv("LJ_PRIM_MIN_LANES")) a.prim_min_lanes = atoi(e);
-    if (const char *e = getenv("LJ_REFILL")) a.refill_threshold = atoi(e);
-    a.track_refill = 24;
-    if (const char *e = getenv("LJ_TRACK_REFILL")) a.track_refill = atoi(e);
-    a.shadow_chunk = 128;
-    if (const char *e = getenv("LJ_SHADOW_CHUNK")) a.shadow_chunk = std::max(32, atoi(e));
-    a.trav_min = 4;
-    if (const char *e = getenv("LJ_TRAV_MIN")) a.trav_min = std::max(1, atoi(e));
-    a.chunk = 64;
-    if (const char *e = getenv("LJ_CHUNK")) a.chunk = std::max(32, atoi(e));
+    a.tiles_x = tiles_x;
+    a.tiles_y = tiles_y;
+    a.tile_stride = tile_stride;
+    a.tile_offset = opts.tile_offset;
+    a.tiles_local = tiles_local;
+    a.total_items = total_items;
+    fill_trace_args(s, a);
     // (k_shade is compiled for 4 resident CTAs per SM, 124 registers: caps of 5 / 6 / 8 CTAs spilled and were slower)
 
-    const int nb256 = (capacity + 255) / 256, nb128 = (capacity + 127) / 128;
-    // persistent grid: exactly one wave of resident CTAs (SM count x the occupancy of k_trace)
-    static int trace_blocks = 0, walk_blocks = 1, step_blocks = 1, flight_blocks = 1;
-    if (trace_blocks == 0) {
-#if defined(LJ_HOSTSIM)
-        trace_blocks = 1;
-#else
-        int sms = 0, a0 = 0, a1 = 0, a2 = 0;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a0, k_trace<0>, 128, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a1, k_trace<1>, 128, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a2, k_trace<2>, 128, 0);
-        trace_blocks = std::max(1, sms) * std::max(1, std::min(a0, a1));
-        walk_blocks = std::max(1, sms) * std::max(1, a2);
-        int a3 = 0, a4 = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a4, k_trace<3>, 128, 0);
-        step_blocks = std::max(1, sms) * std::max(1, a4);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a3, k_flight, 128, 0);
-        flight_blocks = std::max(1, sms) * std::max(1, a3);
-#endif
-    }
+    const int nb256 = ((int)capacity + 255) / 256, nb128 = ((int)capacity + 127) / 128;
+    const LaunchGeom &g = s->geom;
     unsigned int *d_cursors = s->d_cursors;
-    a.cursors = d_cursors;
     EventPool evp(s->event_pool);
     std::vector<cudaEvent_t> marks;  // 5 per wave: before regen, extend, shade, shadow, after shadow
     uint64_t launches = 0, waves = 0;
@@ -749,15 +1053,16 @@ static int render_impl(lj_scene *s, const lj_render_opts *opts_in, float *d_out,
         LJ_CUDA(cudaEventRecord(ev_copied[queued % kRing], stream));
         launches++;
         if (queued >= (uint64_t)kLookahead) {
-            uint64_t w = queued - kLookahead;
-            LJ_CUDA(cudaEventSynchronize(ev_copied[w % kRing]));
-            if (h_active[w % kRing] == 0) { waves = w; marks.push_back(e0); marks.push_back(e1); marks.push_back(nullptr); break; }
+            uint64_t wv = queued - kLookahead;
+            LJ_CUDA(cudaEventSynchronize(ev_copied[wv % kRing]));
+            if (h_active[wv % kRing] == 0) { waves = wv; marks.push_back(e0); marks.push_back(e1); marks.push_back(nullptr); break; }
         }
         LJ_CUDA(cudaMemsetAsync(d_cursors, 0, 4 * sizeof(unsigned int), stream));
-        LJ_LAUNCH(k_trace<0>, trace_blocks, 128, stream, sc, a);
+        if (vol) LJ_LAUNCH(k_trace<0>, g.trace_blocks, 128, stream, sc, a);
+        else launch_trace(s, a, 0, stream);
         LJ_CUDA(cudaEventRecord(e2, stream));
         if (vol) {
-            if (sc.num_media > 0) { LJ_LAUNCH(k_flight, flight_blocks, 128, stream, sc, a); launches++; }
+            if (sc.num_media > 0) { LJ_LAUNCH(k_flight, g.flight_blocks, 128, stream, sc, a); launches++; }
             LJ_LAUNCH(k_shade_vol, nb128, 128, stream, sc, a);
         } else if (s->has_disney) {
             LJ_LAUNCH((k_shade<4, true>), nb128, 128, stream, sc, a);
@@ -765,9 +1070,9 @@ static int render_impl(lj_scene *s, const lj_render_opts *opts_in, float *d_out,
             LJ_LAUNCH((k_shade<4, false>), nb128, 128, stream, sc, a);
         }
         LJ_CUDA(cudaEventRecord(e3, stream));
-        if (vol && s->has_grid_media) LJ_LAUNCH(k_trace<3>, step_blocks, 128, stream, sc, a);
-        else if (vol) LJ_LAUNCH(k_trace<2>, walk_blocks, 128, stream, sc, a);
-        else LJ_LAUNCH(k_trace<1>, trace_blocks, 128, stream, sc, a);
+        if (vol && s->has_grid_media) LJ_LAUNCH(k_trace<3>, g.step_blocks, 128, stream, sc, a);
+        else if (vol) LJ_LAUNCH(k_trace<2>, g.walk_blocks, 128, stream, sc, a);
+        else launch_trace(s, a, 1, stream);
         LJ_CUDA(cudaEventRecord(e4, stream));
         launches += 3;
         queued++;
@@ -776,8 +1081,10 @@ static int render_impl(lj_scene *s, const lj_render_opts *opts_in, float *d_out,
     }
     auto hp_t2 = std::chrono::steady_clock::now();
     LJ_CUDA(cudaEventRecord(ev_end, stream));
-    LJ_LAUNCH(k_resolve, (npix + 255) / 256, 256, stream, s->d_film, a.film_sq, npix, 1.f / (float)(se - sb), opts.normalize, d_out, d_var);
-    launches++;
+    if (d_out) {
+        LJ_LAUNCH(k_resolve, (npix + 255) / 256, 256, stream, s->d_film, a.film_sq, npix, 1.f / (float)(se - sb), opts.normalize, d_out, d_var);
+        launches++;
+    }
     LJ_CUDA(cudaMemcpyAsync(h_counters, d_counters, sizeof(unsigned long long) * C_TOTAL, cudaMemcpyDeviceToHost, stream));
     LJ_CUDA(cudaStreamSynchronize(stream));
     LJ_CUDA(cudaGetLastError());
@@ -808,14 +1115,124 @@ static int render_impl(lj_scene *s, const lj_render_opts *opts_in, float *d_out,
         stats->closest_rays = h_counters[C_CLOSEST];
         stats->shadow_rays = h_counters[C_SHADOW];
         stats->bounces = h_counters[C_BOUNCES];
-        for (int k = 0; k < kStripes; k++) stats->bounces += h_counters[C_BOUNCES_STRIPED + k];
+        for (int k2 = 0; k2 < kStripes; k2++) stats->bounces += h_counters[C_BOUNCES_STRIPED + k2];
         stats->node_steps = h_counters[C_NODE_STEPS];
         stats->prim_tests = h_counters[C_PRIM_TESTS];
+        stats->node_passes = h_counters[C_NODE_PASSES];
+        stats->prim_passes = h_counters[C_PRIM_PASSES];
         stats->kernel_launches = launches;
         stats->waves = waves;
         stats->extend_launches = stats->shade_launches = stats->shadow_launches = waves;
         stats->regen_launches = waves + 1;
+        stats->pool_paths = (uint64_t)capacity;
     }
+    return LJ_OK;
+}
+
+// ---- query seam S2 through the wavefront kernels: a ray batch is loaded into the path pool the way k_regen / k_shade
+// leave it and traced by the kernels lj_render launches (same grid, same cursors, same scheduling), so the ray-parity
+// tests cover the refill / compaction / postponing logic and not only the plain per-thread loop of api.cu.
+__global__ void k_pool_load_rays(PathPool pool, const lj_ray *rays, int m, int stride, int shadow, float shadow_eps) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool has = false;
+    if (i < pool.capacity) {
+        int k = i / stride;
+        has = (i % stride) == 0 && k < m;
+        V4 meta = mk4(0, 0, 0, 0), sh_d = mk4(0, 0, 0, -1.f);
+        if (has) {
+            lj_ray r = rays[k];
+            meta = mk4(u2f((uint32_t)k), u2f(1u | kAlive | kOccupied), 0, 0);
+            if (shadow) {
+                // a path that continued: the NEE segment starts at ray_o (k_trace<1>); hit / ray_d are not read
+                pool.ray_o[i] = mk4(r.org[0], r.org[1], r.org[2], shadow_eps);
+                pool.ray_d[i] = mk4(0, 0, 1, 0);
+                sh_d = mk4(r.dir[0], r.dir[1], r.dir[2], r.tfar);
+                pool.sh_c[i] = mk4(1, 0, 0, 0);
+            } else {
+                pool.ray_o[i] = mk4(r.org[0], r.org[1], r.org[2], r.tnear);
+                pool.ray_d[i] = mk4(r.dir[0], r.dir[1], r.dir[2], r.tfar);
+            }
+        }
+        pool.meta[i] = meta;
+        pool.sh_d[i] = sh_d;
+        pool.rad[i] = mk4(0, 0, 0, 1.f);
+        pool.hit[i] = mk4(0, 0, 0, u2f((uint32_t)kNoHit));
+    }
+    if (shadow) {
+        unsigned mask = __ballot_sync(0xffffffffu, has);
+        if (LJ_LANE() == 0 && i < pool.capacity) pool.sh_mask[i / LJ_WARP_WIDTH] = mask;
+    }
+}
+__global__ void k_pool_store_hits(const LJ_GRID_CONSTANT DevScene sc, PathPool pool, int m, int stride, lj_hit *hits, uint8_t *occluded) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= m) return;
+    size_t i = (size_t)k * stride;
+    if (occluded) { occluded[k] = pool.rad[i].x == 0.f ? 1 : 0; return; }
+    V4 h = pool.hit[i], o = pool.ray_o[i], d = pool.ray_d[i];
+    Hit hit;
+    hit.t = h.x; hit.u = h.y; hit.v = h.z; hit.prim = (int)f2u(h.w);
+    if (hit.prim == kNoHit) hit.t = d.w;  // a miss reports the ray's tfar, like lj_trace_closest
+    lj_hit out;
+    hit_to_abi(sc, xyz(o), xyz(d), hit, out);
+    hits[k] = out;
+}
+
+static int trace_pool_impl(lj_scene *s, const lj_ray *rays, int64_t n, const lj_trace_opts *opts, lj_hit *hits, uint8_t *occluded, double *kernel_ms) {
+    const bool shadow = occluded != nullptr;
+    const int stride = opts->slot_stride > 1 ? opts->slot_stride : 1;
+    if (shadow)
+        for (int64_t i = 0; i < n; i++)
+            if (rays[i].tnear != s->dev.shadow_eps) { set_error("the shadow kernel starts every segment at the scene's shadow epsilon: rays[].tnear must equal it"); return LJ_ERR_INVALID; }
+    long long capacity = opts->pool_paths > 0 ? opts->pool_paths : std::min<long long>((long long)n * stride, 1 << 22);
+    capacity = std::max<long long>(1024, (capacity + 255) / 256 * 256);
+    const int per_round = (int)((capacity + stride - 1) / stride);
+    int r = ensure_pool(s, (int)capacity, false);
+    if (r != LJ_OK) return r;
+    r = ensure_render_buffers(s, s->dev.camera.width * s->dev.camera.height, false);
+    if (r != LJ_OK) return r;
+    WaveArgs a;
+    memset(&a, 0, sizeof(a));
+    a.pool = s->pool;
+    fill_trace_args(s, a);
+    lj_ray *d_rays = nullptr;
+    lj_hit *d_hits = nullptr;
+    uint8_t *d_occ = nullptr;
+    cudaStream_t stream = s->stream;
+    auto cleanup = [&]() { lj_dev_free(d_rays); lj_dev_free(d_hits); lj_dev_free(d_occ); };
+    cudaError_t e = lj_dev_alloc((void **)&d_rays, (size_t)per_round * sizeof(lj_ray));
+    if (e == cudaSuccess && !shadow) e = lj_dev_alloc((void **)&d_hits, (size_t)per_round * sizeof(lj_hit));
+    if (e == cudaSuccess && shadow) e = lj_dev_alloc((void **)&d_occ, (size_t)per_round);
+    if (e != cudaSuccess) { cleanup(); return cuda_fail(e, "ray batch allocation"); }
+    const int saved_kernel = opts->kernel;
+    double total_ms = 0;
+    const int nb256 = ((int)capacity + 255) / 256;
+    for (int64_t done = 0; done < n && e == cudaSuccess; done += per_round) {
+        const int m = (int)std::min<int64_t>(per_round, n - done);
+        e = cudaMemcpyAsync(d_rays, rays + done, (size_t)m * sizeof(lj_ray), cudaMemcpyHostToDevice, stream);
+        if (e != cudaSuccess) break;
+        LJ_LAUNCH(k_pool_load_rays, nb256, 256, stream, s->pool, d_rays, m, stride, shadow ? 1 : 0, s->dev.shadow_eps);
+        cudaMemsetAsync(s->d_cursors, 0, 4 * sizeof(unsigned int), stream);
+        cudaMemsetAsync(s->d_counters, 0, sizeof(unsigned long long) * C_TOTAL, stream);
+        cudaEventRecord(s->ev[0], stream);
+        if (saved_kernel == LJ_TRACE_WAVEFRONT) {
+            if (shadow) LJ_LAUNCH(k_trace_q<1>, s->geom.q_blocks, kQWarps * LJ_WARP_WIDTH, stream, s->dev, a);
+            else LJ_LAUNCH(k_trace_q<0>, s->geom.q_blocks, kQWarps * LJ_WARP_WIDTH, stream, s->dev, a);
+        } else {
+            if (shadow) LJ_LAUNCH(k_trace<1>, s->geom.trace_blocks, 128, stream, s->dev, a);
+            else LJ_LAUNCH(k_trace<0>, s->geom.trace_blocks, 128, stream, s->dev, a);
+        }
+        cudaEventRecord(s->ev[1], stream);
+        LJ_LAUNCH(k_pool_store_hits, (m + 255) / 256, 256, stream, s->dev, s->pool, m, stride, d_hits, d_occ);
+        if (shadow) e = cudaMemcpyAsync(occluded + done, d_occ, (size_t)m, cudaMemcpyDeviceToHost, stream);
+        else e = cudaMemcpyAsync(hits + done, d_hits, (size_t)m * sizeof(lj_hit), cudaMemcpyDeviceToHost, stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        float ms = 0;
+        if (e == cudaSuccess) { cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]); total_ms += ms; }
+    }
+    cleanup();
+    if (e != cudaSuccess) return cuda_fail(e, "wavefront ray batch");
+    if (kernel_ms) *kernel_ms = total_ms;
     return LJ_OK;
 }
 
@@ -823,21 +1240,45 @@ static int render_impl(lj_scene *s, const lj_render_opts *opts_in, float *d_out,
 
 using namespace lj;
 
+extern "C" int lj_trace_closest_ex(lj_scene *s, const lj_ray *rays, int64_t n, const lj_trace_opts *opts, lj_hit *hits, double *kernel_ms) {
+    if (!s || !rays || !hits || n < 0) { set_error("invalid argument"); return LJ_ERR_INVALID; }
+    if (!opts || opts->kernel == LJ_TRACE_PLAIN) return lj_trace_closest(s, rays, n, hits, kernel_ms);
+    if (opts->kernel != LJ_TRACE_WAVEFRONT && opts->kernel != LJ_TRACE_WAVEFRONT_LANE) { set_error("unknown trace kernel"); return LJ_ERR_INVALID; }
+    if (n == 0) return LJ_OK;
+    DeviceGuard guard(s->device);
+    return trace_pool_impl(s, rays, n, opts, hits, nullptr, kernel_ms);
+}
+
+extern "C" int lj_trace_any_ex(lj_scene *s, const lj_ray *rays, int64_t n, const lj_trace_opts *opts, uint8_t *occluded, double *kernel_ms) {
+    if (!s || !rays || !occluded || n < 0) { set_error("invalid argument"); return LJ_ERR_INVALID; }
+    if (!opts || opts->kernel == LJ_TRACE_PLAIN) return lj_trace_any(s, rays, n, occluded, kernel_ms);
+    if (opts->kernel != LJ_TRACE_WAVEFRONT && opts->kernel != LJ_TRACE_WAVEFRONT_LANE) { set_error("unknown trace kernel"); return LJ_ERR_INVALID; }
+    if (n == 0) return LJ_OK;
+    DeviceGuard guard(s->device);
+    return trace_pool_impl(s, rays, n, opts, nullptr, occluded, kernel_ms);
+}
+
 extern "C" int lj_render_device(lj_scene *s, const lj_render_opts *opts, float *d_out_rgb, void *stream, lj_stats *stats) {
     if (!s || !d_out_rgb) { set_error("null argument"); return LJ_ERR_INVALID; }
     if (opts && opts->variance_out) { set_error("variance_out needs lj_render (host buffers)"); return LJ_ERR_INVALID; }
+    if (opts && opts->num_gpus > 1) { set_error("lj_render_device renders on the scene's primary device: use lj_render for the multi-GPU split"); return LJ_ERR_INVALID; }
+    DeviceGuard guard(s->device);
     return render_impl(s, opts, d_out_rgb, nullptr, stream ? (cudaStream_t)stream : s->stream, stats);
 }
 
 extern "C" int lj_render(lj_scene *s, const lj_render_opts *opts, float *out_rgb, lj_stats *stats) {
     if (!s || !out_rgb) { set_error("null argument"); return LJ_ERR_INVALID; }
+    DeviceGuard guard(s->device);
     int npix = s->dev.camera.width * s->dev.camera.height;
-    const bool host_prof = getenv("LJ_PROFILE_HOST") != nullptr;
+    const bool host_prof = tuning().host_prof;
     auto t0 = std::chrono::steady_clock::now();
     float *d_out = nullptr, *d_var = nullptr;
     LJ_CUDA(lj_dev_alloc((void **)&d_out, (size_t)npix * 3 * sizeof(float)));
     bool want_var = opts && opts->variance_out;
-    if (want_var) LJ_CUDA(lj_dev_alloc((void **)&d_var, (size_t)npix * 3 * sizeof(float)));
+    if (want_var) {
+        cudaError_t e = lj_dev_alloc((void **)&d_var, (size_t)npix * 3 * sizeof(float));
+        if (e != cudaSuccess) { lj_dev_free(d_out); return cuda_fail(e, "variance buffer allocation"); }
+    }
     auto t1 = std::chrono::steady_clock::now();
     int r = render_impl(s, opts, d_out, d_var, s->stream, stats);
     auto t2 = std::chrono::steady_clock::now();

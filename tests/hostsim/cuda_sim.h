@@ -17,6 +17,7 @@
 #define __forceinline__ inline
 #define __launch_bounds__(...)
 #define __restrict__
+#define __shared__ static
 #define LJ_GRID_CONSTANT
 #define LJ_LANE() 0
 #define LJ_WARP_WIDTH 1
@@ -81,6 +82,7 @@ inline unsigned __reduce_add_sync(unsigned, unsigned v) { return v; }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 inline void __threadfence() {}
+inline void __syncwarp() {}
 using std::max;
 using std::min;
 inline float lj_warp_min(float x) { return x; }

@@ -192,6 +192,8 @@ SCENE_XML = {
     "sponza": "sponza/sponza.xml",
     "matpreview": "matpreview/matpreview.xml",
     "pixel_filter_test": "pixel_filter_test/pixel_filter_test.xml",
+    "pixel_filter_box": "pixel_filter_test/pixel_filter_box.xml",    # generated by oracle/Makefile (box / tent rfilter)
+    "pixel_filter_tent": "pixel_filter_test/pixel_filter_tent.xml",
     "disney_bsdf": "disney_bsdf_test/disney_bsdf.xml",
     "disney_diffuse": "disney_bsdf_test/disney_diffuse.xml",
     "disney_metal": "disney_bsdf_test/disney_metal.xml",

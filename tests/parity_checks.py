@@ -66,6 +66,38 @@ def check_occlusion_parity(scene, ref, rays, min_agree=0.9999):
     return float(agree)
 
 
+def check_wavefront_trace(scene, ref, rays, shadow, configs, min_agree=0.9999):
+    """The persistent traversal kernels of the renderer (rays loaded into the path pool, lj_trace_*_ex) against
+    (i) the plain per-thread loop: bit-identical primitive, t, u, v / occlusion flag -- the step functions and the
+    equal-t tie policy are shared, so scheduling must not change any answer -- and (ii) the oracle, at the
+    north_star bars (through check_ray_parity / check_occlusion_parity of the plain result they are identical to).
+    configs: (kernel, pool_paths, slot_stride) tuples -- full, sparse and non-multiple-of-chunk pools."""
+    from lajolla_public_b200 import abi
+    out = {}
+    if shadow:
+        base = scene.occluded(rays)
+        assert (base == ref.occluded(rays)).mean() >= min_agree
+        for kernel, pool, stride in configs:
+            got = scene.occluded(rays, kernel=kernel, pool_paths=pool, slot_stride=stride)
+            assert np.array_equal(got, base), f"occlusion differs from the plain loop: kernel {kernel} pool {pool} stride {stride}: {(got != base).sum()} of {base.size}"
+        out["occluded_frac"] = float(base.mean())
+    else:
+        base = scene.intersect_hits(rays)
+        h2 = ref.intersect_hits(rays)
+        same = (base["shape_id"] == h2["shape_id"]) & (base["primitive_id"] == h2["primitive_id"])
+        assert same.mean() >= min_agree
+        for kernel, pool, stride in configs:
+            got = scene.intersect_hits(rays, kernel=kernel, pool_paths=pool, slot_stride=stride)
+            for f in ("shape_id", "primitive_id"):
+                assert np.array_equal(got[f], base[f]), f"{f} differs from the plain loop: kernel {kernel} pool {pool} stride {stride}: {(got[f] != base[f]).sum()} of {base.size}"
+            for f in ("t", "u", "v"):
+                assert np.array_equal(got[f].view(np.uint32), base[f].view(np.uint32)), f"{f} not bit-identical: kernel {kernel} pool {pool} stride {stride}"
+        out["hit_frac"] = float((base["shape_id"] >= 0).mean())
+    out["n"] = int(rays.shape[0])
+    out["configs"] = len(configs)
+    return out
+
+
 def shadow_rays(ref, rays, seed=3):
     """Segments from hit points towards sampled light points, as path_tracing.h:124-128 builds them."""
     rng = np.random.default_rng(seed)

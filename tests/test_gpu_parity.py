@@ -54,6 +54,45 @@ def test_ray_parity(oracle, name):
     record("ray_parity", dict(scene=name, primary=r1, bounce=r2, occlusion_agree=occ))
 
 
+@pytest.mark.parametrize("name", ["cbox", "sponza", "disney_bsdf", "vol_cbox_teapot"])
+def test_wavefront_kernels_ray_parity(oracle, name):
+    """Parity test 1 on the kernels that actually render: k_trace_q<0|1> (queue form, the path integrator's) and
+    k_trace<0|1> (lane form) fed through the path pool exactly as lj_render launches them, with pools that are full,
+    sparse (every 7th / 37th slot), smaller than the batch (several rounds) and not a multiple of the fetch chunk."""
+    from lajolla_public_b200 import abi
+    sc, ref = pair(oracle, name)
+    n = 1 << 17
+    rays = pc.primary_rays(ref, n + 13)
+    Q, L = abi.LJ_TRACE_WAVEFRONT, abi.LJ_TRACE_WAVEFRONT_LANE
+    cfg = [(Q, 0, 1), (Q, 0, 7), (Q, 1 << 15, 1), (Q, 50000, 37), (Q, 1000, 1), (L, 0, 1), (L, 0, 37), (L, 50000, 3)]
+    r1 = pc.check_wavefront_trace(sc, ref, rays, False, cfg)
+    r2 = pc.check_wavefront_trace(sc, ref, pc.bounce_rays(ref, rays), False, cfg)
+    r3 = pc.check_wavefront_trace(sc, ref, pc.shadow_rays(ref, rays), True, cfg)
+    record("wavefront_ray_parity", dict(scene=name, primary=r1, bounce=r2, shadow=r3))
+
+
+@pytest.mark.parametrize("name", ["pixel_filter_test", "pixel_filter_box", "pixel_filter_tent"])
+def test_pixel_filters(oracle, name):
+    """filters/{gaussian,box,tent}.inl on the device: sample_primary ray parity (the filter offset is a function of
+    the sub-pixel position, camera.cpp:27-33) and a render of the 1000x-checkerboard floor, whose pixel means depend
+    on the filter footprint, against the reference's render()."""
+    sc, ref = pair(oracle, name)
+    pc.check_camera_parity(sc, ref)
+    img, var = sc.render(spp=64, variance=True)
+    ref_img, _ = ref.render(spp=64)
+    st = pc.image_stats(img, ref_img)
+    record("pixel_filter", dict(scene=name, **{k: (float(v) if np.isscalar(v) else v) for k, v in st.items() if np.isscalar(v)}))
+    m, rm = img.mean(axis=(0, 1)), ref_img.mean(axis=(0, 1))
+    assert np.allclose(m, rm, rtol=0.02), (m, rm)
+    # the filters differ visibly on this scene: a box / tent render must be closer to its own reference than to the
+    # gaussian scene's (guards against the filter type being ignored)
+    if name != "pixel_filter_test":
+        _, gref = pair(oracle, "pixel_filter_test")
+        g_img, _ = gref.render(spp=64)
+        blur = lambda a: a.reshape(60, 8, 80, 8, 3).mean(axis=(1, 3))
+        assert np.abs(blur(img) - blur(ref_img)).mean() <= np.abs(blur(img) - blur(g_img)).mean() + 1e-4
+
+
 @pytest.mark.parametrize("name", SCENES)
 def test_vertex_camera_light_parity(oracle, name):
     sc, ref = pair(oracle, name)

@@ -48,6 +48,24 @@ def test_ray_parity(oracle, name):
     pc.check_occlusion_parity(sc, ref, pc.shadow_rays(ref, rays))
 
 
+@pytest.mark.parametrize("name", ["pixel_filter_box", "pixel_filter_tent"])
+def test_pixel_filter_camera_parity(oracle, name):
+    sc, ref = pair(oracle, name)
+    pc.check_camera_parity(sc, ref)
+
+
+def test_wavefront_kernels_ray_parity(oracle):
+    """The persistent traversal kernels (queue form and lane form) through the serial stand-in: state machine,
+    refill and result write-back; the warp-level compaction itself only runs on the GPU (-m gpu repeats this)."""
+    from lajolla_public_b200 import abi
+    sc, ref = pair(oracle, "cbox")
+    rays = pc.primary_rays(ref, 1500)
+    cfg = [(abi.LJ_TRACE_WAVEFRONT, 0, 1), (abi.LJ_TRACE_WAVEFRONT, 1000, 3), (abi.LJ_TRACE_WAVEFRONT_LANE, 0, 1), (abi.LJ_TRACE_WAVEFRONT_LANE, 1024, 5)]
+    pc.check_wavefront_trace(sc, ref, rays, False, cfg)
+    pc.check_wavefront_trace(sc, ref, pc.bounce_rays(ref, rays), False, cfg)
+    pc.check_wavefront_trace(sc, ref, pc.shadow_rays(ref, rays), True, cfg)
+
+
 @pytest.mark.parametrize("name", SCENES)
 def test_vertex_camera_light_parity(oracle, name):
     sc, ref = pair(oracle, name)
