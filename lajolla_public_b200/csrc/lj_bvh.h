@@ -165,12 +165,16 @@ LJ_HD uint32_t sign_extend_s8x4(uint32_t v) {
 }
 // 1 + q / 32768 for byte i of v: the byte is dropped into the mantissa of 1.0f with one PRMT (full-rate ALU)
 // instead of a shift, a mask and an I2F (quarter-rate conversion pipe, 48 of them per node otherwise).
+// `one` is 0x3f800000.  The persistent kernels pass it in from a kernel PARAMETER (WaveArgs::one_bits) so that the
+// compiler has to hold it in a register: PRMT takes a single immediate, and with a compile-time constant there the
+// selector was materialised into a register for every byte (48 extra moves per node step, profiles/r02a_*); with the
+// constant in a register the selector is the immediate and the 48 PRMTs share one register.
 template <int I>
-LJ_HD float byte_m(uint32_t v) {
+LJ_HD float byte_m(uint32_t v, uint32_t one) {
 #if defined(__CUDA_ARCH__)
-    return __uint_as_float(__byte_perm(v, 0x3f800000u, 0x7604u | (I << 4)));
+    return __uint_as_float(__byte_perm(v, one, 0x7604u | (I << 4)));
 #else
-    return u2f(0x3f800000u | (((v >> (8 * I)) & 0xffu) << 8));
+    return u2f(one | (((v >> (8 * I)) & 0xffu) << 8));
 #endif
 }
 constexpr float kByteScale = 32768.0f;
@@ -209,6 +213,21 @@ LJ_HD V3 trav_idir(V3 d) {
                1.0f / (fabsf(d.y) > tiny ? d.y : copysignf(tiny, d.y)),
                1.0f / (fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z)));
 }
+// the same with the hardware's approximate reciprocal (1 ulp; one MUFU instead of the ~12-instruction IEEE division):
+// for kernels that recompute 1/d at every node step instead of keeping it (k_trace_q)
+LJ_HD V3 trav_idir_fast(V3 d) {
+#if defined(__CUDA_ARCH__)
+    const float tiny = 8.271806e-25f;
+    float x = fabsf(d.x) > tiny ? d.x : copysignf(tiny, d.x), y = fabsf(d.y) > tiny ? d.y : copysignf(tiny, d.y);
+    float z = fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z), rx, ry, rz;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rx) : "f"(x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ry) : "f"(y));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rz) : "f"(z));
+    return mk3(rx, ry, rz);
+#else
+    return trav_idir(d);
+#endif
+}
 LJ_HD void trav_init(Trav &tr, V3 o, V3 d, float tnear, float tfar) {
     tr.o = o; tr.d = d;
     tr.idir = trav_idir(d);
@@ -226,7 +245,7 @@ LJ_HD void trav_init(Trav &tr, V3 o, V3 d, float tnear, float tfar) {
 // Pop the nearest unvisited child of node group tr.G, test its 8 children: the hit internal children
 // become the new tr.G (the rest of the old group is pushed), the hit leaf slots become tr.Gt.
 template <class Stack>
-LJ_HD void trav_node(const DevNode8 *nodes, Trav &tr, Stack &stack) {
+LJ_HD void trav_node(const DevNode8 *nodes, Trav &tr, Stack &stack, const uint32_t one = 0x3f800000u) {
     U2 G = tr.G;
     int bit = bfind32(G.y);
     G.y &= ~(1u << bit);
@@ -245,7 +264,8 @@ LJ_HD void trav_node(const DevNode8 *nodes, Trav &tr, Stack &stack) {
     // The addend carries the rounding of (p - o), of 1/d and of the subtraction of s: an absolute error of
     // 2^-23 (|a| + |s|) that does not shrink with the distance itself (|s| 2^-23 is 0.4 % of one quantisation
     // step).  Near planes are pulled in and far planes pushed out by that much so the test stays conservative.
-    const float kSlabErr = 2.4e-7f;
+    // (3 ulp: one more than the exact-reciprocal analysis, for trav_idir_fast's 1-ulp MUFU.RCP)
+    const float kSlabErr = 3.6e-7f;
     float exn = (fabsf(ox) + fabsf(sx)) * kSlabErr, eyn = (fabsf(oy) + fabsf(sy)) * kSlabErr, ezn = (fabsf(oz) + fabsf(sz)) * kSlabErr;
     float oxn = (ox - sx) - exn, oxf = (ox - sx) + exn, oyn = (oy - sy) - eyn, oyf = (oy - sy) + eyn;
     float ozn = (oz - sz) - ezn, ozf = (oz - sz) + ezn;
@@ -268,9 +288,9 @@ LJ_HD void trav_node(const DevNode8 *nodes, Trav &tr, Stack &stack) {
         uint32_t nearz = nz ? hiz : loz, farz = nz ? loz : hiz;
 #define LJ_CHILD(J)                                                                                         \
         {                                                                                                       \
-            float t0x = fmaf(byte_m<J>(nearx), sx, oxn), t1x = fmaf(byte_m<J>(farx), sx, oxf);                  \
-            float t0y = fmaf(byte_m<J>(neary), sy, oyn), t1y = fmaf(byte_m<J>(fary), sy, oyf);                  \
-            float t0z = fmaf(byte_m<J>(nearz), sz, ozn), t1z = fmaf(byte_m<J>(farz), sz, ozf);                  \
+            float t0x = fmaf(byte_m<J>(nearx, one), sx, oxn), t1x = fmaf(byte_m<J>(farx, one), sx, oxf);        \
+            float t0y = fmaf(byte_m<J>(neary, one), sy, oyn), t1y = fmaf(byte_m<J>(fary, one), sy, oyf);        \
+            float t0z = fmaf(byte_m<J>(nearz, one), sz, ozn), t1z = fmaf(byte_m<J>(farz, one), sz, ozf);        \
             float tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tr.tnear));                                            \
             float tf = fminf(fminf(t1x, t1y), fminf(t1z, tmax_ray));                                            \
             /* conservative: widen the far side by a few ulp (Ize, "Robust BVH ray traversal") */              \

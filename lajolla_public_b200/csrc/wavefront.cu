@@ -45,6 +45,7 @@ struct WaveArgs {
     // k_trace_q: per-warp scratch stacks (qdepth entries x kQRays rays x 8 B per warp) and its refill threshold
     U2 *qstack;
     int qdepth, q_refill, q_chunk;
+    uint32_t one_bits;  // 0x3f800000, see byte_m (lj_bvh.h)
     // image-space split (lj_render_opts.split == LJ_SPLIT_TILES): this call renders the 8x4 pixel tiles t with
     // t % tile_stride == tile_offset; a sample split leaves tile_stride = 1
     int tile_stride, tile_offset, tiles_local;
@@ -319,7 +320,7 @@ __global__ void __launch_bounds__(128, MODE >= 2 ? LJ_WALK_MIN_BLOCKS : (MODE ==
                     }
                     if (descend) {
                         node_steps++;
-                        trav_node(sc.nodes8, tr, tr.stack);
+                        trav_node(sc.nodes8, tr, tr.stack, a.one_bits);
                     }
                 }
                 trav_next_group(tr, tr.stack);
@@ -457,12 +458,12 @@ __global__ void __launch_bounds__(kQWarps * LJ_WARP_WIDTH, 8) k_trace_q(const LJ
     q.status[lane] = Q_EMPTY;
     q.status[lane + W] = Q_EMPTY;
     __syncwarp();
+    int cF = 0;  // warp-uniform: slots waiting for their result to be written
     for (unsigned pass = 0;; pass++) {
         uint32_t s0 = q.status[lane], s1 = q.status[lane + W];
         const unsigned mN0 = __ballot_sync(0xffffffffu, s0 == Q_NODE), mN1 = __ballot_sync(0xffffffffu, s1 == Q_NODE);
         const unsigned mP0 = __ballot_sync(0xffffffffu, s0 == Q_PRIM), mP1 = __ballot_sync(0xffffffffu, s1 == Q_PRIM);
-        const unsigned mF0 = __ballot_sync(0xffffffffu, s0 == Q_FIN), mF1 = __ballot_sync(0xffffffffu, s1 == Q_FIN);
-        const int cN = __popc(mN0) + __popc(mN1), cP = __popc(mP0) + __popc(mP1), cF = __popc(mF0) + __popc(mF1);
+        const int cN = __popc(mN0) + __popc(mN1), cP = __popc(mP0) + __popc(mP1);
         const int live = cN + cP;
         const bool want_refill = !drained && live < a.q_refill;
         int kind;
@@ -544,6 +545,7 @@ __global__ void __launch_bounds__(kQWarps * LJ_WARP_WIDTH, 8) k_trace_q(const LJ
                 }
             }
             __syncwarp();
+            cF = __popc(__ballot_sync(0xffffffffu, q.status[lane] == Q_FIN)) + __popc(__ballot_sync(0xffffffffu, q.status[lane + W] == Q_FIN));
             continue;
         } else if (live == 0) {
             break;  // pool exhausted, nothing in flight, nothing left to write
@@ -552,18 +554,27 @@ __global__ void __launch_bounds__(kQWarps * LJ_WARP_WIDTH, 8) k_trace_q(const LJ
             const int fN = cN < W ? cN : W, fP = cP < W ? cP : W;
             kind = fP >= fN ? Q_PRIM : Q_NODE;
         }
-        // ---- compaction: the first W slots that want this kind of step, the two halves taking turns to go first
+        // ---- compaction: the first W slots that want this kind of step, the two halves taking turns to go first.  Slots
+        // r and r + W share a shared-memory bank, so of the second half the lanes whose first-half slot is NOT selected
+        // go first: the 32 selected slots then sit in 32 different banks whenever that is possible.
         {
-            const unsigned m0 = kind == Q_NODE ? mN0 : (kind == Q_PRIM ? mP0 : mF0);
-            const unsigned m1 = kind == Q_NODE ? mN1 : (kind == Q_PRIM ? mP1 : mF1);
+            unsigned m0, m1;
+            if (kind == Q_FIN) { m0 = __ballot_sync(0xffffffffu, s0 == Q_FIN); m1 = __ballot_sync(0xffffffffu, s1 == Q_FIN); }
+            else { m0 = kind == Q_NODE ? mN0 : mP0; m1 = kind == Q_NODE ? mN1 : mP1; }
             const bool flip = (pass & 1u) != 0;
             const unsigned first = flip ? m1 : m0, second = flip ? m0 : m1;
-            const int cf = __popc(first);
-            if ((first >> lane) & 1u) { int r = __popc(first & lt); if (r < W) q.list[r] = (uint32_t)(lane + (flip ? W : 0)); }
-            if ((second >> lane) & 1u) { int r = cf + __popc(second & lt); if (r < W) q.list[r] = (uint32_t)(lane + (flip ? 0 : W)); }
+            const unsigned pref = second & ~first, rest = second & first;
+            const int cf = __popc(first), cp = __popc(pref);
+            if ((first >> lane) & 1u) q.list[__popc(first & lt)] = (uint32_t)(lane + (flip ? W : 0));
+            if ((second >> lane) & 1u) {
+                const int r = cf + (((pref >> lane) & 1u) ? __popc(pref & lt) : cp + __popc(rest & lt));
+                if (r < W) q.list[r] = (uint32_t)(lane + (flip ? 0 : W));
+            }
             __syncwarp();
             const int nsel = cf + __popc(second) < W ? cf + __popc(second) : W;
-            if (lane == 0) { if (kind == Q_NODE) node_passes++; else if (kind == Q_PRIM) prim_passes++; }
+            node_passes += kind == Q_NODE;
+            prim_passes += kind == Q_PRIM;
+            bool finished = false;
             if (lane < nsel) {
                 const int r = (int)q.list[lane];
                 Trav tr;
@@ -592,11 +603,11 @@ __global__ void __launch_bounds__(kQWarps * LJ_WARP_WIDTH, 8) k_trace_q(const LJ
                     stk.base = stack_base + r;
                     stk.stride = kQRays;
                     if (kind == Q_NODE) {
-                        tr.idir = trav_idir(tr.d);
+                        tr.idir = trav_idir_fast(tr.d);
                         const uint32_t oct = (tr.d.x < 0 ? 1u : 0u) | (tr.d.y < 0 ? 2u : 0u) | (tr.d.z < 0 ? 4u : 0u);
                         tr.octinv4 = (7u ^ oct) * 0x01010101u;
                         node_steps++;
-                        trav_node(sc.nodes8, tr, stk);
+                        trav_node(sc.nodes8, tr, stk, a.one_bits);
                     } else {
                         tr.Gt.x = q.Tx[r]; tr.Gt.y = q.Ty[r];
                         prim_tests++;
@@ -607,9 +618,13 @@ __global__ void __launch_bounds__(kQWarps * LJ_WARP_WIDTH, 8) k_trace_q(const LJ
                     trav_next_group(tr, stk);
                     q.Gx[r] = tr.G.x; q.Gy[r] = tr.G.y; q.Tx[r] = tr.Gt.x; q.Ty[r] = tr.Gt.y;
                     q.sp[r] = (uint32_t)tr.sp;
-                    q.status[r] = q_status_of(tr);
+                    const uint32_t st = q_status_of(tr);
+                    q.status[r] = st;
+                    finished = st == Q_FIN;
                 }
             }
+            if (kind == Q_FIN) cF -= nsel;
+            else cF += __popc(__ballot_sync(0xffffffffu, finished));  // (the ballot also orders the shared-memory writes)
             __syncwarp();
         }
     }
@@ -922,6 +937,7 @@ static void fill_trace_args(lj_scene *s, WaveArgs &a) {
     a.chunk = t.chunk;
     a.q_refill = std::min(t.q_refill, kQRays);  // (the host simulation has 2 ray slots per "warp")
     a.q_chunk = t.q_chunk;
+    a.one_bits = 0x3f800000u;
     a.qstack = (U2 *)s->d_qstack;
     a.qdepth = s->qdepth;
     a.cursors = s->d_cursors;
