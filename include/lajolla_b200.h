@@ -310,6 +310,8 @@ typedef struct lj_scene_info {
     double bvh_build_ms, upload_ms, prep_ms;
     double sah_cost;
     int64_t device_bytes;
+    int32_t num_prim_refs; /* BVH leaf entries: > num_prims when large triangles were split spatially */
+    int32_t _pad;
 } lj_scene_info;
 int lj_scene_get_info(lj_scene *scene, lj_scene_info *info);
 /* Light table as built on the device (scene.cpp:48-52): pmf[num_lights], cdf[num_lights+1]. */

@@ -139,7 +139,7 @@ class lj_scene_info(C.Structure):
     _fields_ = [("num_prims", i32), ("num_triangles", i32), ("num_spheres", i32), ("num_bvh_nodes", i32),
                 ("bvh_width", i32), ("bvh_depth", i32), ("bounds_lo", f32 * 3), ("bounds_hi", f32 * 3), ("bsphere_radius", f32),
                 ("bsphere_center", f32 * 3), ("shadow_epsilon", f32), ("bvh_build_ms", f64), ("upload_ms", f64),
-                ("prep_ms", f64), ("sah_cost", f64), ("device_bytes", i64)]
+                ("prep_ms", f64), ("sah_cost", f64), ("device_bytes", i64), ("num_prim_refs", i32), ("_pad", i32)]
 
 
 # symbol -> (restype, argtypes); every function include/lajolla_b200.h declares.

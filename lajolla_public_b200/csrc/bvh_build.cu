@@ -34,12 +34,16 @@ __host__ __device__ __forceinline__ float float_from_order_key(int k) {
 #endif
 }
 
-__global__ void k_prim_boxes(const LJ_GRID_CONSTANT DevScene sc, const int *prim_shape, const int *prim_local, int n,
+__global__ void k_prim_boxes(const LJ_GRID_CONSTANT DevScene sc, const int *prim_shape, const int *prim_local, const float *ref_box, int n,
                              DevPrim *prims_unsorted, Box3 *boxes, int *scene_bounds /*6 ordered ints*/) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     Box3 b = box_empty();
     if (i < n) {
         prims_unsorted[i] = make_prim(sc, prim_shape[i], prim_local[i], b);
+        if (ref_box) {  // a split reference: the clipped box (inside the primitive's own box by construction)
+            b.lo = mk3(ref_box[6 * i], ref_box[6 * i + 1], ref_box[6 * i + 2]);
+            b.hi = mk3(ref_box[6 * i + 3], ref_box[6 * i + 4], ref_box[6 * i + 5]);
+        }
         boxes[i] = b;
     }
     // warp reduce then one atomic per warp per component
@@ -130,7 +134,7 @@ static cudaError_t exclusive_scan(void *tmp, size_t &tmp_bytes, const int *in, i
 #endif
 }
 
-cudaError_t build_bvh8(const DevScene &sc, const int *d_prim_shape, const int *d_prim_local, int n,
+cudaError_t build_bvh8(const DevScene &sc, const int *d_prim_shape, const int *d_prim_local, const float *d_ref_box, int n,
                        cudaStream_t stream, BvhResult *out) {
     // search radius of the PLOC neighbour search: LJ_PLOC_RADIUS in [1, 64] (default 32)
     int radius = 32;
@@ -169,7 +173,7 @@ cudaError_t build_bvh8(const DevScene &sc, const int *d_prim_shape, const int *d
     CK(cudaMemsetAsync(d_sah, 0, sizeof(double), stream));
     CK(cudaMemsetAsync(nodes, 0, sizeof(DevNode8) * max_nodes8, stream));
 
-    LJ_LAUNCH(k_prim_boxes, nb, T, stream, sc, d_prim_shape, d_prim_local, n, prims_unsorted, boxes, scene_bounds);
+    LJ_LAUNCH(k_prim_boxes, nb, T, stream, sc, d_prim_shape, d_prim_local, d_ref_box, n, prims_unsorted, boxes, scene_bounds);
     LJ_LAUNCH(k_morton, nb, T, stream, boxes, n, scene_bounds, keys, vals);
 #if defined(LJ_HOSTSIM)
     {

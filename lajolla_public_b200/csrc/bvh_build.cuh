@@ -19,8 +19,11 @@ struct BvhResult {
     int launches = 0;
 };
 
-// sc must already carry the device pointers of shapes / positions / indices.
-cudaError_t build_bvh8(const DevScene &sc, const int *d_prim_shape, const int *d_prim_local, int n,
+// sc must already carry the device pointers of shapes / positions / indices.  The n entries of prim_shape / prim_local
+// are primitive REFERENCES: a large triangle may appear several times, each time with its own box in d_ref_box (6
+// floats: lo.xyz, hi.xyz; the part of the triangle inside one cell of a spatial split, scene.cu split_references);
+// d_ref_box == nullptr: one reference per primitive, boxes computed from the primitives.
+cudaError_t build_bvh8(const DevScene &sc, const int *d_prim_shape, const int *d_prim_local, const float *d_ref_box, int n,
                        cudaStream_t stream, BvhResult *out);
 
 }  // namespace lj

@@ -631,8 +631,8 @@ __global__ void __launch_bounds__(kQWarps * LJ_WARP_WIDTH, 8) k_trace_q(const LJ
     warp_add(&a.counters[MODE == 0 ? C_CLOSEST : C_SHADOW], traced);
     warp_add(&a.counters[C_NODE_STEPS], node_steps);
     warp_add(&a.counters[C_PRIM_TESTS], prim_tests);
-    warp_add(&a.counters[C_NODE_PASSES], node_passes);
-    warp_add(&a.counters[C_PRIM_PASSES], prim_passes);
+    warp_add(&a.counters[C_NODE_PASSES], lane == 0 ? node_passes : 0u);  // (warp-uniform counters)
+    warp_add(&a.counters[C_PRIM_PASSES], lane == 0 ? prim_passes : 0u);
 }
 
 
