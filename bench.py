@@ -175,6 +175,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--split", default="spp", choices=["spp", "tiles"])
+    ap.add_argument("--backend", default="nccl", choices=["nccl", "gloo"], help="diagnostic: gloo reduces the film through host memory")
+    ap.add_argument("--no-reduce", action="store_true", help="diagnostic: skip the film reduction (the image stays split across ranks)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -195,7 +197,10 @@ def main():
         os.environ["NCCL_DEBUG"] = "WARN"  # NCCL prints its version banner on stdout, which must carry exactly one JSON line
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        if args.backend == "nccl":
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        else:
+            dist.init_process_group("gloo")
 
     key, full_spp, cpu_spp = WORKLOADS[args.workload]
     spp = args.spp or full_spp
@@ -226,7 +231,8 @@ def main():
         st = scene.render_device(film.data_ptr(), stream.cuda_stream, spp=total_spp, sample_begin=s_begin,
                                  sample_end=s_end, normalize=False, pool_paths=args.pool,
                                  tile_stride=tile_stride, tile_offset=tile_offset)
-        partition.reduce_film(film, dist, 0)  # the one collective
+        if not args.no_reduce:
+            partition.reduce_film(film, dist, 0)  # the one collective
         return st
 
     def barrier():

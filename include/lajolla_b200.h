@@ -200,8 +200,11 @@ typedef struct lj_stats {
     double reduce_ms;          /* multi-GPU: film reduction on the primary device */
 } lj_stats;
 
-/* Selects the CUDA device for the calling thread; LJ_ERR_NO_DEVICE if there is none. */
-int lj_init(int device);
+/* Names the CUDA devices the library may use.  device_ids[0] is the PRIMARY device: it becomes
+ * current on the calling thread, scenes are created on it and multi-GPU renders are reduced on it; lj_scene_create
+ * replicates every scene on the other devices.  device_ids == NULL: devices 0 .. num_devices-1; num_devices <= 0: one
+ * device.  LJ_ERR_NO_DEVICE if there is no CUDA device (the library has no CPU path). */
+int lj_init(const int *device_ids, int num_devices);
 const char *lj_last_error(void);
 
 /* Uploads the description, builds the BVH (replaces rtcNewScene..rtcCommitScene, scene.cpp:20-27),

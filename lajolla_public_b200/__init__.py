@@ -64,9 +64,14 @@ class Scene:
     """Device-resident scene (the reference's `Scene`, scene.h:39-88): BVH, mip chains and sampling
     tables are built on the GPU by lj_scene_create."""
 
-    def __init__(self, desc: ljs.SceneDesc, device: int = 0):
+    def __init__(self, desc: ljs.SceneDesc, device=0):
+        """device: one CUDA device index, or a list -- the first is the primary device, the scene is replicated on the
+        others and render(num_gpus=...) splits the work among them inside the library."""
         self._lib = load_library()
-        abi.check(self._lib.lj_init(device))
+        ids = [int(device)] if np.isscalar(device) else [int(d) for d in device]
+        self.devices = ids
+        arr = (C.c_int32 * len(ids))(*ids)
+        abi.check(self._lib.lj_init(arr, len(ids)))
         cdesc, keep = ljs.to_c(desc)
         h = C.c_void_p()
         abi.check(self._lib.lj_scene_create(C.byref(cdesc), C.byref(h)))

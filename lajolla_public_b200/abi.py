@@ -144,7 +144,7 @@ class lj_scene_info(C.Structure):
 
 # symbol -> (restype, argtypes); every function include/lajolla_b200.h declares.
 PROTOTYPES = {
-    "lj_init": (C.c_int, [C.c_int]),
+    "lj_init": (C.c_int, [pi32, C.c_int]),
     "lj_last_error": (C.c_char_p, []),
     "lj_scene_create": (C.c_int, [C.POINTER(lj_scene_desc), C.POINTER(C.c_void_p)]),
     "lj_scene_destroy": (None, [C.c_void_p]),

@@ -4,6 +4,7 @@
 #include "scene.cuh"
 
 #include <mutex>
+#include <thread>
 
 #include <math.h>
 #include <string.h>
@@ -292,7 +293,18 @@ void pool_block_give(int device, void *block, size_t bytes) {
 
 extern "C" const char *lj_last_error(void) { return g_error.c_str(); }
 
-extern "C" int lj_init(int device) {
+namespace lj {
+// devices handed to lj_init, in order; [0] is the primary device (scenes are created there, multi-GPU renders are
+// reduced there).  Process-wide, set once per lj_init call.
+static std::mutex g_devices_mutex;
+static std::vector<int> g_devices;
+std::vector<int> init_devices() {
+    std::lock_guard<std::mutex> lock(g_devices_mutex);
+    return g_devices;
+}
+}  // namespace lj
+
+extern "C" int lj_init(const int *device_ids, int num_devices) {
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0) {
@@ -300,24 +312,38 @@ extern "C" int lj_init(int device) {
         set_error("no CUDA device visible: libljb200 has no CPU path");
         return LJ_ERR_NO_DEVICE;
     }
-    if (device < 0 || device >= count) { set_error("device index out of range"); return LJ_ERR_INVALID; }
-    LJ_CUDA(cudaSetDevice(device));
-    LJ_CUDA(cudaFree(0));
-#if !defined(LJ_HOSTSIM)
-    {   // keep freed blocks in the stream-ordered pool (see lj_dev_alloc)
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-            unsigned long long keep = ~0ull;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        }
-        cudaGetLastError();
+    std::vector<int> ids;
+    if (num_devices <= 0) ids.push_back(device_ids ? device_ids[0] : 0);
+    else for (int i = 0; i < num_devices; i++) ids.push_back(device_ids ? device_ids[i] : i);
+    for (size_t i = 0; i < ids.size(); i++) {
+        if (ids[i] < 0 || ids[i] >= count) { set_error("device index out of range"); return LJ_ERR_INVALID; }
+        for (size_t j = 0; j < i; j++) if (ids[j] == ids[i]) { set_error("duplicate device index"); return LJ_ERR_INVALID; }
     }
+    for (size_t i = ids.size(); i-- > 0;) {  // (the primary device last, so that it stays current)
+        LJ_CUDA(cudaSetDevice(ids[i]));
+        LJ_CUDA(cudaFree(0));
+#if !defined(LJ_HOSTSIM)
+        {   // keep freed blocks in the stream-ordered pool (see lj_dev_alloc)
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, ids[i]) == cudaSuccess) {
+                unsigned long long keep = ~0ull;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            cudaGetLastError();
+        }
 #endif
+    }
+    {
+        std::lock_guard<std::mutex> lock(g_devices_mutex);
+        g_devices = ids;
+    }
     return LJ_OK;
 }
 
 extern "C" void lj_scene_destroy(lj_scene *s) {
     if (!s) return;
+    for (lj_scene *r : s->replicas) lj_scene_destroy(r);
+    s->replicas.clear();
     DeviceGuard guard(s->device);
     cudaDeviceSynchronize();  // the caller's streams may still read the tables
     for (void *p : s->allocations) lj_dev_free(p);
@@ -334,8 +360,8 @@ extern "C" void lj_scene_destroy(lj_scene *s) {
     delete s;
 }
 
-extern "C" int lj_scene_create(const lj_scene_desc *desc, lj_scene **out) {
-    if (!desc || !out) { set_error("null argument"); return LJ_ERR_INVALID; }
+// builds the scene on the CURRENT device of the calling thread
+static int scene_create_here(const lj_scene_desc *desc, lj_scene **out) {
     *out = nullptr;
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
@@ -711,5 +737,42 @@ extern "C" int lj_scene_get_mip_level(lj_scene *s, int32_t channels, int32_t ima
         LJ_CUDA(cudaMemcpy(tmp.data(), s->dev.texels3 + d.offset[level], n * sizeof(V4), cudaMemcpyDeviceToHost));
         for (size_t k = 0; k < n; k++) { data[3 * k] = tmp[k].x; data[3 * k + 1] = tmp[k].y; data[3 * k + 2] = tmp[k].z; }
     }
+    return LJ_OK;
+}
+
+extern "C" int lj_scene_create(const lj_scene_desc *desc, lj_scene **out) {
+    if (!desc || !out) { set_error("null argument"); return LJ_ERR_INVALID; }
+    int r = scene_create_here(desc, out);
+    if (r != LJ_OK) return r;
+#if !defined(LJ_HOSTSIM)
+    // one replica per further device of lj_init (the scene is replicated on every GPU), built
+    // concurrently, one host thread per device.  A single-device lj_init (or a scene created on a device that is not
+    // the primary one) has none.
+    std::vector<int> devs = init_devices();
+    lj_scene *primary = *out;
+    if (devs.size() > 1 && devs[0] == primary->device) {
+        const size_t n = devs.size() - 1;
+        std::vector<lj_scene *> reps(n, nullptr);
+        std::vector<int> codes(n, LJ_OK);
+        std::vector<std::string> errors(n);
+        std::vector<std::thread> threads;
+        for (size_t k = 0; k < n; k++)
+            threads.emplace_back([&, k] {
+                if (cudaSetDevice(devs[k + 1]) != cudaSuccess) { codes[k] = LJ_ERR_CUDA; errors[k] = "cudaSetDevice failed"; return; }
+                codes[k] = scene_create_here(desc, &reps[k]);
+                if (codes[k] != LJ_OK) errors[k] = lj_last_error();
+            });
+        for (auto &t : threads) t.join();
+        for (size_t k = 0; k < n; k++)
+            if (codes[k] != LJ_OK) {
+                for (lj_scene *rp : reps) if (rp) lj_scene_destroy(rp);
+                lj_scene_destroy(primary);
+                *out = nullptr;
+                set_error("replica on device " + std::to_string(devs[k + 1]) + ": " + errors[k]);
+                return codes[k];
+            }
+        primary->replicas = reps;
+    }
+#endif
     return LJ_OK;
 }

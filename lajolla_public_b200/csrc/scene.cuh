@@ -39,6 +39,8 @@ struct lj_scene {
     int qdepth = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {};
+    std::vector<lj_scene *> replicas;  // the same scene on the other devices of lj_init (owned; empty on a replica)
+    bool peer_checked = false, peer_ok = false;  // the primary device can read the replicas' films directly
 };
 
 namespace lj {
@@ -76,6 +78,7 @@ struct DeviceGuard {
 void *pool_block_take(int device, size_t bytes, size_t *got_bytes);
 void pool_block_give(int device, void *block, size_t bytes);
 void set_error(const std::string &msg);
+std::vector<int> init_devices();  // the device list of the last lj_init
 int cuda_fail(cudaError_t e, const char *what);
 }  // namespace lj
 

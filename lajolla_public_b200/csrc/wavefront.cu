@@ -18,7 +18,14 @@
 
 #include <algorithm>
 #include <chrono>
+#include <mutex>
+#include <string>
+#include <thread>
 #include <vector>
+
+#if !defined(LJ_HOSTSIM)
+#include <dlfcn.h>
+#endif
 
 namespace lj {
 
@@ -1141,6 +1148,7 @@ static int render_impl(lj_scene *s, const lj_render_opts *opts_in, float *d_out,
         stats->extend_launches = stats->shade_launches = stats->shadow_launches = waves;
         stats->regen_launches = waves + 1;
         stats->pool_paths = (uint64_t)capacity;
+        stats->gpus_used = 1;
     }
     return LJ_OK;
 }
@@ -1282,9 +1290,243 @@ extern "C" int lj_render_device(lj_scene *s, const lj_render_opts *opts, float *
     return render_impl(s, opts, d_out_rgb, nullptr, stream ? (cudaStream_t)stream : s->stream, stats);
 }
 
+// ---- multi-GPU render inside the library -------------------------------------------------------------
+// The scene is replicated on every device of lj_init (lj_scene_create); lj_render(num_gpus = G) gives each of G devices
+// a share of the samples -- a contiguous block of the per-pixel sample indices (LJ_SPLIT_SPP) or every G-th 8x4 pixel
+// tile (LJ_SPLIT_TILES) -- renders the shares concurrently, one host thread per GPU, and sums the per-GPU films on the
+// primary device.  Two reductions: LJ_REDUCE_P2P, one kernel on the primary device that LOADS the other devices' films
+// through their peer mappings (NVLink) while it resolves -- reduce and resolve fused, no staging copy; LJ_REDUCE_NCCL,
+// ncclReduce of the fp32 films to the primary device, then the usual resolve.
+#if !defined(LJ_HOSTSIM)
+constexpr int kMaxGpus = 16;
+struct FilmSet { const float *film[kMaxGpus]; const float *film_sq[kMaxGpus]; int n; };
+
+__global__ void k_resolve_multi(const LJ_GRID_CONSTANT FilmSet fs, int npix, float inv_n, int normalize, float *out, float *var_out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    float4 f = make_float4(0, 0, 0, 0), q = make_float4(0, 0, 0, 0);
+    for (int g = 0; g < fs.n; g++) {  // (peer loads for g > 0: 16 bytes per pixel per GPU over NVLink)
+        float4 v = reinterpret_cast<const float4 *>(fs.film[g])[i];
+        f.x += v.x; f.y += v.y; f.z += v.z; f.w += v.w;
+        if (var_out) { float4 w = reinterpret_cast<const float4 *>(fs.film_sq[g])[i]; q.x += w.x; q.y += w.y; q.z += w.z; }
+    }
+    float s = normalize ? inv_n : 1.f;
+    out[3 * i] = f.x * s; out[3 * i + 1] = f.y * s; out[3 * i + 2] = f.z * s;
+    if (var_out) {
+        float n = f.w, v[3] = {0, 0, 0};
+        if (n > 1) {
+            v[0] = fmaxf(q.x - f.x * f.x / n, 0.f) / (n - 1) / n;
+            v[1] = fmaxf(q.y - f.y * f.y / n, 0.f) / (n - 1) / n;
+            v[2] = fmaxf(q.z - f.z * f.z / n, 0.f) / (n - 1) / n;
+        }
+        var_out[3 * i] = v[0]; var_out[3 * i + 1] = v[1]; var_out[3 * i + 2] = v[2];
+    }
+}
+
+// NCCL is loaded at run time, and only when a render asks for it: libljb200.so must load next to any NCCL the host
+// process already carries (PyTorch bundles its own) without pulling a second copy in at link time.
+struct NcclApi {
+    void *lib = nullptr;
+    int (*CommInitAll)(void **, int, const int *) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*Reduce)(const void *, void *, size_t, int, int, int, void *, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    std::vector<void *> comms;
+    std::vector<int> devices;
+};
+static std::mutex g_nccl_mutex;
+static NcclApi g_nccl;
+
+static int nccl_prepare(const std::vector<int> &devices) {
+    if (!g_nccl.lib) {
+        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) { set_error(std::string("LJ_REDUCE_NCCL: cannot load libnccl.so.2: ") + dlerror()); return LJ_ERR_UNSUPPORTED; }
+        g_nccl.lib = h;
+        *(void **)&g_nccl.CommInitAll = dlsym(h, "ncclCommInitAll");
+        *(void **)&g_nccl.CommDestroy = dlsym(h, "ncclCommDestroy");
+        *(void **)&g_nccl.GroupStart = dlsym(h, "ncclGroupStart");
+        *(void **)&g_nccl.GroupEnd = dlsym(h, "ncclGroupEnd");
+        *(void **)&g_nccl.Reduce = dlsym(h, "ncclReduce");
+        *(void **)&g_nccl.GetErrorString = dlsym(h, "ncclGetErrorString");
+        if (!g_nccl.CommInitAll || !g_nccl.CommDestroy || !g_nccl.GroupStart || !g_nccl.GroupEnd || !g_nccl.Reduce) {
+            set_error("LJ_REDUCE_NCCL: libnccl lacks the expected entry points");
+            return LJ_ERR_UNSUPPORTED;
+        }
+    }
+    if (g_nccl.devices != devices) {
+        for (void *c : g_nccl.comms) g_nccl.CommDestroy(c);
+        g_nccl.comms.assign(devices.size(), nullptr);
+        int r = g_nccl.CommInitAll(g_nccl.comms.data(), (int)devices.size(), devices.data());
+        if (r != 0) {
+            g_nccl.comms.clear(); g_nccl.devices.clear();
+            set_error(std::string("ncclCommInitAll: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"));
+            return LJ_ERR_CUDA;
+        }
+        g_nccl.devices = devices;
+    }
+    return LJ_OK;
+}
+
+static int render_multi(lj_scene *s, const lj_render_opts *opts_in, int G, float *out_rgb, lj_stats *stats) {
+    lj_render_opts base;
+    memset(&base, 0, sizeof(base));
+    if (opts_in) base = *opts_in;
+    const DevScene &sc = s->dev;
+    if (sc.options.integrator != LJ_INT_PATH && sc.options.integrator != LJ_INT_VOLPATH) G = 1;  // one launch: nothing to split
+    if (base.tile_stride > 1) { set_error("tile_stride / tile_offset and num_gpus > 1 exclude each other"); return LJ_ERR_INVALID; }
+    const int spp = base.spp > 0 ? base.spp : sc.options.spp;
+    int sb = base.sample_begin, se = base.sample_end;
+    if (sb == 0 && se == 0) se = spp;
+    if (sb < 0 || se > spp || sb >= se) { set_error("bad sample range"); return LJ_ERR_INVALID; }
+    int split = base.split;
+    if (split == LJ_SPLIT_AUTO) split = (se - sb) >= G ? LJ_SPLIT_SPP : LJ_SPLIT_TILES;
+    if (split == LJ_SPLIT_SPP && (se - sb) < G) G = se - sb;
+    std::vector<lj_scene *> sc_g(G);
+    sc_g[0] = s;
+    for (int g = 1; g < G; g++) sc_g[g] = s->replicas[g - 1];
+    const int npix = sc.camera.width * sc.camera.height;
+    const bool want_var = base.variance_out != nullptr;
+    // peer access from the primary device to the replicas' films (once per scene)
+    if (!s->peer_checked) {
+        s->peer_checked = true;
+        s->peer_ok = true;
+        for (lj_scene *r : s->replicas) {
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, s->device, r->device) != cudaSuccess || !can) { s->peer_ok = false; break; }
+            cudaError_t e = cudaDeviceEnablePeerAccess(r->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { s->peer_ok = false; break; }
+        }
+        cudaGetLastError();
+    }
+    int reduce = base.reduce;
+    if (reduce == LJ_REDUCE_AUTO) reduce = s->peer_ok ? LJ_REDUCE_P2P : LJ_REDUCE_NCCL;
+    if (reduce == LJ_REDUCE_P2P && !s->peer_ok) { set_error("LJ_REDUCE_P2P: the primary device cannot access its peers"); return LJ_ERR_UNSUPPORTED; }
+    if (reduce != LJ_REDUCE_P2P && reduce != LJ_REDUCE_NCCL) { set_error("unknown reduce mode"); return LJ_ERR_INVALID; }
+    // ---- the shares, one host thread per GPU
+    std::vector<lj_stats> st(G);
+    std::vector<int> codes(G, LJ_OK);
+    std::vector<std::string> errors(G);
+    std::vector<float *> d_dummy_var(G, nullptr);
+    auto work = [&](int g) {
+        lj_scene *sg = sc_g[g];
+        DeviceGuard guard(sg->device);
+        lj_render_opts o = base;
+        o.spp = spp;
+        o.normalize = 0;
+        o.variance_out = nullptr;
+        o.num_gpus = 1;
+        if (split == LJ_SPLIT_SPP) {
+            const int total = se - sb, per = total / G, extra = total % G;
+            o.sample_begin = sb + g * per + std::min(g, extra);
+            o.sample_end = o.sample_begin + per + (g < extra ? 1 : 0);
+            o.tile_stride = 0; o.tile_offset = 0;
+        } else {
+            o.sample_begin = sb; o.sample_end = se;
+            o.tile_stride = G; o.tile_offset = g;
+        }
+        // render_impl accumulates into sg->d_film (and d_film_sq when a variance buffer is named); no resolve here
+        float *var_flag = nullptr;
+        if (want_var) {
+            if (lj_dev_alloc((void **)&d_dummy_var[g], 16) != cudaSuccess) { codes[g] = LJ_ERR_CUDA; errors[g] = "allocation failed"; return; }
+            var_flag = d_dummy_var[g];
+        }
+        codes[g] = render_impl(sg, &o, nullptr, var_flag, sg->stream, &st[g]);
+        if (codes[g] != LJ_OK) errors[g] = lj_last_error();
+    };
+    {
+        std::vector<std::thread> threads;
+        for (int g = 1; g < G; g++) threads.emplace_back(work, g);
+        work(0);
+        for (auto &t : threads) t.join();
+    }
+    for (int g = 0; g < G; g++) if (d_dummy_var[g]) { DeviceGuard guard(sc_g[g]->device); lj_dev_free(d_dummy_var[g]); }
+    for (int g = 0; g < G; g++)
+        if (codes[g] != LJ_OK) { set_error("GPU " + std::to_string(sc_g[g]->device) + ": " + errors[g]); return codes[g]; }
+    // ---- reduce on the primary device
+    float *d_out = nullptr, *d_var = nullptr;
+    LJ_CUDA(lj_dev_alloc((void **)&d_out, (size_t)npix * 3 * sizeof(float)));
+    if (want_var) {
+        cudaError_t e = lj_dev_alloc((void **)&d_var, (size_t)npix * 3 * sizeof(float));
+        if (e != cudaSuccess) { lj_dev_free(d_out); return cuda_fail(e, "variance buffer allocation"); }
+    }
+    cudaStream_t stream = s->stream;
+    const float inv_n = 1.f / (float)(se - sb);
+    cudaEventRecord(s->ev[2], stream);
+    int rc = LJ_OK;
+    if (reduce == LJ_REDUCE_P2P) {
+        FilmSet fs;
+        fs.n = G;
+        for (int g = 0; g < G; g++) { fs.film[g] = sc_g[g]->d_film; fs.film_sq[g] = sc_g[g]->d_film_sq; }
+        LJ_LAUNCH(k_resolve_multi, (npix + 255) / 256, 256, stream, fs, npix, inv_n, base.normalize, d_out, d_var);
+    } else {
+        std::lock_guard<std::mutex> lock(g_nccl_mutex);
+        std::vector<int> devs(G);
+        for (int g = 0; g < G; g++) devs[g] = sc_g[g]->device;
+        rc = nccl_prepare(devs);
+        if (rc == LJ_OK) {
+            for (int pass = 0; pass < (want_var ? 2 : 1) && rc == LJ_OK; pass++) {
+                g_nccl.GroupStart();
+                for (int g = 0; g < G; g++) {
+                    float *buf = pass == 0 ? sc_g[g]->d_film : sc_g[g]->d_film_sq;
+                    int r = g_nccl.Reduce(buf, buf, (size_t)npix * 4, 7 /*ncclFloat32*/, 0 /*ncclSum*/, 0, g_nccl.comms[g], sc_g[g]->stream);
+                    if (r != 0) { set_error(std::string("ncclReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error")); rc = LJ_ERR_CUDA; }
+                }
+                g_nccl.GroupEnd();
+            }
+            if (rc == LJ_OK) LJ_LAUNCH(k_resolve, (npix + 255) / 256, 256, stream, s->d_film, want_var ? s->d_film_sq : nullptr, npix, inv_n, base.normalize, d_out, d_var);
+        }
+    }
+    cudaEventRecord(s->ev[3], stream);
+    if (rc == LJ_OK) {
+        cudaError_t e = cudaStreamSynchronize(stream);
+        for (int g = 1; g < G && e == cudaSuccess; g++) { DeviceGuard guard(sc_g[g]->device); e = cudaStreamSynchronize(sc_g[g]->stream); }
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpy(out_rgb, d_out, (size_t)npix * 3 * sizeof(float), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && want_var) e = cudaMemcpy(base.variance_out, d_var, (size_t)npix * 3 * sizeof(float), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = cuda_fail(e, "film reduction");
+    }
+    if (rc == LJ_OK && stats) {
+        memset(stats, 0, sizeof(*stats));
+        for (int g = 0; g < G; g++) {
+            const lj_stats &x = st[g];
+            stats->render_ms = std::max(stats->render_ms, x.render_ms);
+            stats->extend_ms = std::max(stats->extend_ms, x.extend_ms); stats->shadow_ms = std::max(stats->shadow_ms, x.shadow_ms);
+            stats->shade_ms = std::max(stats->shade_ms, x.shade_ms); stats->regen_ms = std::max(stats->regen_ms, x.regen_ms);
+            stats->samples += x.samples; stats->closest_rays += x.closest_rays; stats->shadow_rays += x.shadow_rays; stats->bounces += x.bounces;
+            stats->kernel_launches += x.kernel_launches; stats->waves = std::max(stats->waves, x.waves);
+            stats->extend_launches += x.extend_launches; stats->shadow_launches += x.shadow_launches;
+            stats->shade_launches += x.shade_launches; stats->regen_launches += x.regen_launches;
+            stats->node_steps += x.node_steps; stats->prim_tests += x.prim_tests; stats->node_passes += x.node_passes; stats->prim_passes += x.prim_passes;
+            stats->pool_paths += x.pool_paths;
+        }
+        stats->kernel_launches += 1;
+        stats->gpus_used = G;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, s->ev[2], s->ev[3]);
+        stats->reduce_ms = ms;
+    }
+    lj_dev_free(d_out);
+    if (d_var) lj_dev_free(d_var);
+    return rc;
+}
+#endif
+
 extern "C" int lj_render(lj_scene *s, const lj_render_opts *opts, float *out_rgb, lj_stats *stats) {
     if (!s || !out_rgb) { set_error("null argument"); return LJ_ERR_INVALID; }
     DeviceGuard guard(s->device);
+#if !defined(LJ_HOSTSIM)
+    {   // GPUs for this call: 0 = every device lj_init named (the scene's replicas), n = at most n of them
+        const int have = 1 + (int)s->replicas.size();
+        int want = opts ? opts->num_gpus : 1;
+        if (want < 0 || want > kMaxGpus) { set_error("bad num_gpus"); return LJ_ERR_INVALID; }
+        if (want > have) { set_error("num_gpus exceeds the devices given to lj_init before this scene was created"); return LJ_ERR_INVALID; }
+        const int G = want == 0 ? have : want;
+        if (G > 1) return render_multi(s, opts, G, out_rgb, stats);
+    }
+#endif
     int npix = s->dev.camera.width * s->dev.camera.height;
     const bool host_prof = tuning().host_prof;
     auto t0 = std::chrono::steady_clock::now();

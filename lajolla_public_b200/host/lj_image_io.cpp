@@ -155,7 +155,7 @@ struct JpegDecoder {
             } else {
                 k += r;
                 unsigned zig = kDezigzag[k++];
-                data[zig] = (short)(extend_receive(s) * dequant[c.tq][k - 1]);
+                data[zig] = (short)(extend_receive(s) * dequant[c.tq][zig]);  // (the table is stored de-zigzagged)
             }
         } while (k < 64);
         return true;

@@ -50,7 +50,7 @@ def test_no_device_is_an_error_not_a_fallback():
     if torch.cuda.is_available():
         pytest.skip("a GPU is present")
     lib = abi.load_library()
-    assert lib.lj_init(0) == abi.LJ_ERR_NO_DEVICE
+    assert lib.lj_init(None, 1) == abi.LJ_ERR_NO_DEVICE
     assert b"no CPU path" in lib.lj_last_error()
     import lajolla_public_b200 as lj
     from lajolla_public_b200 import ljs

@@ -8,7 +8,7 @@ import lajolla_public_b200 as lj, oracle_lib
 from lajolla_public_b200 import ljs, abi
 name = sys.argv[1] if len(sys.argv) > 1 else "sponza"
 desc = ljs.load(oracle_lib.scene_ljs(name))
-lib = lj.load_library(); abi.check(lib.lj_init(0))
+lib = lj.load_library(); abi.check(lib.lj_init(None, 1))
 for i in range(6):
     t0 = time.perf_counter(); cdesc, keep = ljs.to_c(desc); t1 = time.perf_counter()
     h = C.c_void_p(); abi.check(lib.lj_scene_create(C.byref(cdesc), C.byref(h))); t2 = time.perf_counter()
