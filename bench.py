@@ -196,6 +196,10 @@ def main():
     if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
         os.environ["NCCL_DEBUG"] = "WARN"  # NCCL prints its version banner on stdout, which must carry exactly one JSON line
     if world > 1:
+        # The one collective of a step is a 5 MB film reduce: in-switch reduction (NVLS) buys it nothing, and a process
+        # in which NCCL has set NVLS up runs k_trace_q<0> 18 % slower (measured, profiles/r02e_nccl_nvls.txt: 353 ->
+        # 396 Msamples/s at N=2 with NVLS off, = 2 x the single-GPU rate).  An explicit setting in the environment wins.
+        os.environ.setdefault("NCCL_NVLS_ENABLE", "0")
         import torch.distributed as dist
         if args.backend == "nccl":
             dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -308,7 +312,7 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(key, w, h, full_spp), "spp_per_gpu": (s_end - s_begin) if tile_stride == 0 else total_spp, "image_spp": total_spp,
                        "l2_policy": f"path pool (4M slots x {224 if key in VOLPATH else 144} B) streams through HBM every wave, larger than the 126 MB L2",
-                       "scene_source": "reference scene flattened to .ljs", "parallelism": f"{args.split}-split x{world} + NCCL reduce" if world > 1 else "single GPU"},
+                       "scene_source": "reference scene flattened to .ljs", "parallelism": f"{args.split}-split x{world} + NCCL reduce (NCCL_NVLS_ENABLE={os.environ.get('NCCL_NVLS_ENABLE', 'default')})" if world > 1 else "single GPU"},
             "mrays_per_s": (agg["closest"] + agg["shadow"]) * world / (ms_total / 1e3) / 1e6,
             "rays_per_sample": (agg["closest"] + agg["shadow"]) / max(agg["samples"], 1),
             "mean_bounces": agg["bounces"] / max(agg["samples"], 1),

@@ -15,7 +15,7 @@ import numpy as np
 from . import abi, ljs
 from .abi import LajollaError, load_library
 
-__all__ = ["Scene", "parse_scene", "render", "LajollaError", "load_library", "abi", "ljs"]
+__all__ = ["Scene", "parse_scene", "load_scene_description", "render", "LajollaError", "load_library", "abi", "ljs"]
 
 RAY_DTYPE = np.dtype([("org", "<f4", 3), ("tnear", "<f4"), ("dir", "<f4", 3), ("tfar", "<f4")])
 HIT_DTYPE = np.dtype([("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("shape_id", "<i4"), ("primitive_id", "<i4")])
@@ -217,19 +217,27 @@ def measure_read_bandwidth(nbytes, iters=20):
 LAJOLLA_CLI = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lajolla")
 
 
-def parse_scene(path, device: int = 0) -> Scene:
-    """parse_scene() of the reference (parsers/parse_scene.cpp:1602).  `.ljs` files are loaded directly;
-    Mitsuba-style XML goes through the C++ host front end (`lajolla --dump-ljs`)."""
+def load_scene_description(path) -> ljs.SceneDesc:
+    """The flat description of a scene file: `.ljs` containers are read directly, Mitsuba-style XML goes through the
+    host front end (`lajolla --dump-ljs`, lajolla_public_b200/host: XML + OBJ / serialized / PLY / image / volume
+    loaders in C++).  Needs no GPU."""
     path = str(path)
     if path.endswith(".ljs"):
-        return Scene(ljs.load(path), device)
+        return ljs.load(path)
     if not os.path.exists(LAJOLLA_CLI):
         raise ImportError(f"{LAJOLLA_CLI} not built (make -C lajolla_public_b200)")
     import tempfile
     with tempfile.TemporaryDirectory() as tmp:
         out = os.path.join(tmp, "scene.ljs")
-        subprocess.run([LAJOLLA_CLI, "--dump-ljs", out, path], check=True, stdout=subprocess.DEVNULL)
-        return Scene(ljs.load(out), device)
+        r = subprocess.run([LAJOLLA_CLI, "--dump-ljs", out, path], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise LajollaError(abi.LJ_ERR_INVALID, r.stderr.strip() or "scene parse failed")
+        return ljs.load(out)
+
+
+def parse_scene(path, device=0) -> Scene:
+    """parse_scene() of the reference (parsers/parse_scene.cpp:1602): scene file -> device-resident Scene."""
+    return Scene(load_scene_description(path), device)
 
 
 def render(scene: Scene, **kw):

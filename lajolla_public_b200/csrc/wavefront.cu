@@ -265,7 +265,13 @@ __global__ void __launch_bounds__(128, MODE >= 2 ? LJ_WALK_MIN_BLOCKS : (MODE ==
                         wk.medium = (int)(mb & 0xffffu) - 1;
                         wk.budget = mb >> 16;
                         wk.shadow_bounces = 0;
-                        wk.rng = pcg_init(((uint64_t)(unsigned)slot << 32) | f2u(pl.w), a.rp.seed);
+                        // the walk's own stream: a function of the PATH (pixel, sample) and of one draw of the path's
+                        // stream (pl.w), never of the slot the path happens to sit in -- renders are reproducible
+                        // whatever the pool size or the split across GPUs
+                        {
+                            const uint64_t path_id = (uint64_t)f2u(a.pool.meta[slot].x) * a.rp.spp_total + f2u(a.pool.aux[slot].z);
+                            wk.rng = pcg_init(path_stream(path_id) + (((uint64_t)f2u(pl.w) << 1) | 1ull), a.rp.seed);
+                        }
                         float tn;
                         nee_walk_segment(sc, wk, tn, seg_tfar);
                         trav_init(tr, wk.pc, wk.dir, tn, seg_tfar);

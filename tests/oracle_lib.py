@@ -200,6 +200,7 @@ SCENE_XML = {
     "disney_glass": "disney_bsdf_test/disney_glass.xml",
     "disney_clearcoat": "disney_bsdf_test/disney_clearcoat.xml",
     "disney_sheen": "disney_bsdf_test/disney_sheen.xml",
+    "disney_bsdf_array": "disney_bsdf_test/disney_bsdf_array.xml",
     "simple_sphere": "disney_bsdf_test/simple_sphere.xml",
     "volpath_test1": "volpath_test/volpath_test1.xml",
     "volpath_test2": "volpath_test/volpath_test2.xml",
@@ -214,6 +215,27 @@ SCENE_XML = {
     "hetvol": "volpath_test/hetvol.xml",
     "hetvol_colored": "volpath_test/hetvol_colored.xml",
 }
+
+
+HANDOUTS = os.path.join(ROOT, "oracle", "_ref", "handouts")
+
+# scene name -> the handout's render of it (handouts/imgs/*.png, copied to oracle/_ref/handouts by oracle/Makefile)
+HANDOUT_IMAGE = {
+    "cbox": "cbox.png", "veach_mi": "veach_mis.png", "sponza": "sponza.png", "matpreview": "matpreview.png",
+    "pixel_filter_test": "gaussian.png", "pixel_filter_box": "box.png", "pixel_filter_tent": "tent.png",
+    "disney_diffuse": "disney_diffuse.png", "disney_metal": "disney_metal.png", "disney_clearcoat": "disney_clearcoat.png",
+    "disney_glass": "disney_glass.png", "disney_sheen": "disney_sheen.png", "disney_bsdf_array": "disney_bsdf.png",
+    "volpath_test1": "volpath_1.png", "volpath_test2": "volpath_2.png", "volpath_test3": "volpath_3.png",
+    "volpath_test4": "volpath_4.png", "volpath_test4_2": "volpath_4_2.png", "volpath_test5": "volpath_5.png",
+    "volpath_test5_2": "volpath_5_2.png", "volpath_test6": "volpath_6.png", "vol_cbox": "volpath_5_cbox.png",
+    "vol_cbox_teapot": "volpath_5_cbox_teapot.png", "hetvol": "hetvol.png", "hetvol_colored": "colored_smoke.png",
+}
+
+
+def handout_image(name):
+    """The handout's LDR render of a scene as float sRGB in [0, 1], (h, w, 3)."""
+    from PIL import Image
+    return np.asarray(Image.open(os.path.join(HANDOUTS, HANDOUT_IMAGE[name])).convert("RGB"), dtype=np.float64) / 255.0
 
 
 def scene_xml(name):

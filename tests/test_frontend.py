@@ -1,0 +1,148 @@
+"""The host front end (lajolla_public_b200/host: `lajolla` CLI) against the reference's own parser: for every scene
+the oracle knows, `lajolla --dump-ljs` of the XML must give the flat description the oracle dumped from the
+reference's parse_scene() of the same file (oracle/_ref/ljs, built by oracle/ref_glue.cpp) -- same tables field for
+field, float values equal to double-vs-float rounding of derived quantities (matrix inverses), and >= 99.5 % of all
+floats bit-identical (decoded textures, meshes, volumes: 100 %).  CPU only: parsing needs no GPU."""
+import os
+import struct
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+import lajolla_public_b200 as lj
+from lajolla_public_b200 import ljs
+import ljs_compare
+import oracle_lib
+
+CLI = lj.LAJOLLA_CLI
+
+
+@pytest.fixture(scope="module")
+def cli():
+    if not os.path.exists(CLI):
+        subprocess.run(["make", "-C", os.path.dirname(CLI), "lajolla"], check=True, stdout=subprocess.DEVNULL)
+    return CLI
+
+
+def dump(cli, xml, out):
+    r = subprocess.run([cli, "--dump-ljs", out, xml], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return ljs.load(out)
+
+
+@pytest.mark.parametrize("name", sorted(oracle_lib.SCENE_XML))
+def test_scene_description_matches_reference_parser(oracle, cli, name, tmp_path):
+    mine = dump(cli, oracle.scene_xml(name), str(tmp_path / "scene.ljs"))
+    ref = ljs.load(oracle.scene_ljs(name))
+    diffs = ljs_compare.compare(mine, ref)
+    assert not diffs, "\n".join(diffs[:20])
+    same, total = ljs_compare.exact_fraction(mine, ref)
+    assert same >= 0.995 * total, (same, total)
+    # decoded assets are bit-identical: texture texels (stb_image / tinyexr conventions), vertices, voxels
+    for a, b in zip(mine.images, ref.images):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    for a, b in zip(mine.shapes, ref.shapes):
+        if a.positions is not None:
+            assert np.array_equal(a.indices, b.indices)
+            assert np.array_equal(a.positions.view(np.uint32), b.positions.view(np.uint32))
+
+
+def test_python_parse_scene_goes_through_the_cli(oracle, cli):
+    """lj.parse_scene(xml) builds the description with the host front end; only the device upload needs a GPU."""
+    desc = lj.load_scene_description(oracle.scene_xml("cbox"))
+    ref = ljs.load(oracle.scene_ljs("cbox"))
+    assert not ljs_compare.compare(desc, ref)
+
+
+def test_errors_are_reported(cli, tmp_path):
+    bad = tmp_path / "bad.xml"
+    bad.write_text("<scene><shape type='cube'/></scene>")
+    r = subprocess.run([cli, "--dump-ljs", str(tmp_path / "o.ljs"), str(bad)], capture_output=True, text=True)
+    assert r.returncode != 0 and "Unknown shape" in r.stderr
+    r = subprocess.run([cli, "--dump-ljs", str(tmp_path / "o.ljs"), str(tmp_path / "missing.xml")], capture_output=True, text=True)
+    assert r.returncode != 0
+    broken = tmp_path / "broken.xml"
+    broken.write_text("<scene><sensor type='perspective'></scene>")
+    r = subprocess.run([cli, "--dump-ljs", str(tmp_path / "o.ljs"), str(broken)], capture_output=True, text=True)
+    assert r.returncode != 0 and "XML parse error" in r.stderr
+
+
+def test_xml_surface(cli, tmp_path):
+    """Appendix A items the shipped scenes do not exercise: <default> substitution, fovAxis, rectangle + flipNormals,
+    point / directional emitters, srgb colours, inline checkerboard, uvscale, rotate / scale / translate order."""
+    xml = tmp_path / "s.xml"
+    xml.write_text("""<?xml version="1.0"?>
+<scene version="0.5.0">
+  <default name="spp" value="7"/>
+  <!-- a comment -->
+  <integrator type="direct"/>
+  <sensor type="perspective">
+    <float name="fov" value="30"/><string name="fovAxis" value="y"/>
+    <transform name="toWorld"><scale x="2"/><rotate y="1" angle="90"/><translate x="1" y="2" z="3"/></transform>
+    <sampler type="independent"><integer name="sampleCount" value="$spp"/></sampler>
+    <film type="hdrfilm"><integer name="width" value="40"/><integer name="height" value="20"/>
+      <string name="filename" value="out.pfm"/><rfilter type="tent"/></film>
+  </sensor>
+  <bsdf type="twosided" id="m0"><bsdf type="roughplastic"><float name="alpha" value="0.04"/><srgb name="diffuseReflectance" value="#ff8000"/></bsdf></bsdf>
+  <shape type="rectangle"><boolean name="flipNormals" value="true"/><ref id="m0"/>
+    <emitter type="area"><spectrum name="radiance" value="2"/></emitter></shape>
+  <shape type="sphere"><point name="center" x="1" y="0" z="0"/><float name="radius" value="0.5"/>
+    <bsdf type="diffuse"><texture name="reflectance" type="checkerboard"><float name="uvscale" value="4"/></texture></bsdf></shape>
+  <emitter type="point"><point name="position" x="0" y="5" z="0"/><rgb name="intensity" value="10"/></emitter>
+  <emitter type="directional"><vector name="direction" x="0" y="-1" z="0"/><rgb name="irradiance" value="1, 2, 3"/></emitter>
+</scene>""")
+    s = dump(cli, str(xml), str(tmp_path / "s.ljs"))
+    assert (s.options.integrator, s.options.max_depth, s.options.samples_per_pixel) == (5, 2, 7)
+    assert (s.camera.width, s.camera.height, s.camera.filter_type) == (40, 20, 1) and s.camera.filter_param == 2.0
+    # fovAxis y: 30 degrees vertical at aspect 2 -> the horizontal fov goes into perspective(): cot(fov_x / 2)
+    fov_x = 2 * np.arctan(np.tan(np.radians(30) / 2) * 2)
+    # cam_to_sample = scale(-.5, -.5 a, 1) translate(-1, -1/a, 0) perspective(fov): entry (0,0) = -0.5 cot(fov_x / 2)
+    assert abs(s.camera.cam_to_sample[0, 0] - (-0.5 / np.tan(fov_x / 2))) < 1e-6
+    # transform order: scale first, then rotate, then translate (each multiplies from the left)
+    p = s.camera.cam_to_world @ np.array([1, 0, 0, 1.0])
+    assert np.allclose(p[:3], [1, 2, 3 - 2], atol=1e-5)  # (2,0,0) rotated 90 deg about y -> (0,0,-2), + (1,2,3)
+    assert len(s.materials) == 4 and len(s.shapes) == 4 and len(s.lights) == 3
+    m = s.materials[0]
+    assert m.type == 1 and abs(m.tex[2].value[0] - 0.2) < 1e-7  # roughness = sqrt(alpha)
+    assert abs(m.eta - 1.49 / 1.000277) < 1e-6
+    srgb = np.array([1.0, 128 / 255, 0.0])
+    lin = np.where(srgb <= 0.04045, srgb / 12.92, ((srgb + 0.055) / 1.055) ** 2.4)
+    assert np.allclose(m.tex[0].value, lin, atol=1e-6)
+    rect = s.shapes[0]
+    assert np.allclose(rect.normals, [[0, 0, -1]] * 4) and rect.area_light_id == 0
+    assert np.allclose(s.lights[0].intensity, np.array([0.9505, 1.0, 1.0888]) @ np.array([[3.240479, -0.969256, 0.055648], [-1.537150, 1.875991, -0.204043], [-0.498535, 0.041556, 1.057311]]) * 2, atol=1e-5)
+    chk = s.materials[1].tex[0]
+    assert chk.kind == 2 and chk.uscale == 4 and chk.vscale == 4 and np.allclose(chk.value, 0.4) and np.allclose(chk.color1, 0.2)
+    point, direc = s.shapes[2], s.shapes[3]
+    assert point.type == 0 and abs(point.radius - 1e-4) < 1e-10 and np.allclose(s.lights[1].intensity, 10 / 1e-8, rtol=1e-5)
+    assert direc.type == 1 and direc.positions.shape == (4, 3) and np.allclose(direc.positions[:, 1], 1000, atol=1e-2)
+    assert np.allclose(s.lights[2].intensity, np.array([1, 2, 3]) * 1e12, rtol=1e-5)
+
+
+def test_image_writers_round_trip(cli, tmp_path):
+    """imwrite: PFM is lossless, EXR is half precision (image.cpp:135-173); both read back through the front end's own
+    readers (an EXR written by `lajolla` used as an envmap texture in a second scene)."""
+    rng = np.random.default_rng(3)
+    img = (rng.random((24, 40, 3)) * 8).astype(np.float32)
+    # the writers and readers are driven through a small helper binary built next to the CLI
+    exe = os.path.join(os.path.dirname(CLI), "build", "image_io_selftest")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-C", os.path.dirname(CLI), "build/image_io_selftest"], check=True, stdout=subprocess.DEVNULL)
+    raw = tmp_path / "in.bin"
+    with open(raw, "wb") as f:
+        f.write(struct.pack("<iii", 40, 24, 3))
+        f.write(img.tobytes())
+    for ext, tol in ((".pfm", 0.0), (".exr", 2.0 ** -11)):
+        out = tmp_path / ("img" + ext)
+        back = tmp_path / ("back" + ext + ".bin")
+        r = subprocess.run([exe, "write", str(raw), str(out)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        r = subprocess.run([exe, "read", str(out), "3", str(back)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        buf = np.fromfile(back, dtype=np.uint8)
+        w, h, c = np.frombuffer(buf[:12], dtype=np.int32)
+        got = np.frombuffer(buf[12:], dtype=np.float32).reshape(h, w, c)
+        assert (w, h, c) == (40, 24, 3)
+        assert np.all(np.abs(got - img) <= tol * np.maximum(np.abs(img), 1e-3)), ext

@@ -1,0 +1,49 @@
+"""External pin: GPU renders against the images printed in the reference's handouts
+(handouts/imgs/*.png -- the instructor's own renders, made with real Embree and the instructor's solutions of the
+Disney BSDF and volumetric path tracing homeworks).  These are the only reference RESULTS that exist for the two
+configurations whose code the public repository ships as stubs, and an Embree-rendered check of the rest.  The
+handout images are 8-bit tone-mapped (clamp + sRGB), so the bounds are loose: mean FLIP, and the mean colour of
+the image."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import flip
+import lajolla_public_b200 as lj
+import oracle_lib
+
+pytestmark = pytest.mark.gpu
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+
+# scene -> (spp of the GPU render, bound on mean FLIP, bound on the relative difference of the mean colour)
+CASES = {
+    "cbox": (256, 0.06, 0.03), "veach_mi": (256, 0.06, 0.03), "sponza": (128, 0.08, 0.04), "matpreview": (128, 0.08, 0.04),
+    "pixel_filter_test": (64, 0.06, 0.03), "pixel_filter_box": (64, 0.06, 0.03), "pixel_filter_tent": (64, 0.06, 0.03),
+    "disney_diffuse": (128, 0.08, 0.04), "disney_metal": (128, 0.08, 0.04), "disney_clearcoat": (128, 0.08, 0.04),
+    "disney_glass": (128, 0.08, 0.04), "disney_sheen": (128, 0.08, 0.04), "disney_bsdf_array": (64, 0.08, 0.04),
+    "volpath_test1": (64, 0.06, 0.03), "volpath_test2": (256, 0.06, 0.03), "volpath_test3": (256, 0.06, 0.03),
+    "volpath_test4": (256, 0.06, 0.03), "volpath_test4_2": (256, 0.06, 0.03), "volpath_test5": (256, 0.06, 0.03),
+    "volpath_test5_2": (256, 0.06, 0.03), "volpath_test6": (256, 0.06, 0.03), "vol_cbox": (256, 0.08, 0.04),
+    "vol_cbox_teapot": (256, 0.08, 0.04), "hetvol": (128, 0.08, 0.04), "hetvol_colored": (128, 0.08, 0.04),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_render_matches_handout_image(oracle, name):
+    spp, flip_bound, mean_bound = CASES[name]
+    ref = oracle_lib.handout_image(name)
+    sc = lj.parse_scene(oracle.scene_ljs(name))
+    img = sc.render(spp=spp)
+    sc.close()
+    assert img.shape == ref.shape, (img.shape, ref.shape)
+    ldr = flip.tonemap(img)
+    f = flip.flip_mean(ref, ldr)
+    m, rm = ldr.mean(axis=(0, 1)), ref.mean(axis=(0, 1))
+    rel = float(np.abs(m - rm).max() / max(rm.max(), 1e-3))
+    os.makedirs(OUT, exist_ok=True)
+    with open(os.path.join(OUT, "handout_parity.jsonl"), "a") as fh:
+        fh.write(json.dumps(dict(scene=name, spp=spp, flip_mean=f, mean=m.tolist(), handout_mean=rm.tolist(), rel_mean_diff=rel)) + "\n")
+    assert f <= flip_bound, f"mean FLIP {f:.4f} > {flip_bound}"
+    assert rel <= mean_bound, f"mean colour {m} vs handout {rm}"
