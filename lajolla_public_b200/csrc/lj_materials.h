@@ -39,11 +39,52 @@ LJ_HD float fresnel_dielectric(float n_dot_i, float eta) {
 }
 
 // microfacet.h:57-81
-LJ_HD float GTR2(float n_dot_h, float roughness) {
-    float alpha = roughness * roughness;
-    float a2 = alpha * alpha;
-    float t = 1 + (a2 - 1) * n_dot_h * n_dot_h;
-    return a2 / (kPi * t * t);
+// The reference evaluates D = a2 / (pi (1 + (a2 - 1) (n.h)^2)^2) in double.  In fp32 that denominator cancels when
+// the half vector is near the normal and alpha is small (veach_mi's alpha = 0.005: a2 = 2.5e-5); a cancellation-free
+// rewrite (sin^2 + a2 cos^2 from the tangential components) is NOT equivalent either, because the fp32 frame the
+// reference is handed is unit / orthogonal only to 1e-7 and its formula sees |n|^2 - 1 at full weight (relative
+// 4e-4 on D at n.h = 0.9998, profiles/r02_bsdf_tail.txt).  So the reference's own expression is evaluated, with the
+// half vector and n.h in fp64 (about a dozen DFMAs and one division per evaluation).
+// (half vector wi + eta wo: eta = 1 for reflection, the relative IOR for refraction, roughdielectric.inl:33-40)
+LJ_HD float GTR2_alpha(V3 n, V3 wi, V3 wo, float eta, float alpha) {
+    double a2 = (double)alpha * (double)alpha;
+    double sx = (double)wi.x + (double)eta * wo.x, sy = (double)wi.y + (double)eta * wo.y, sz = (double)wi.z + (double)eta * wo.z;
+    double ns = sx * n.x + sy * n.y + sz * n.z, ss = sx * sx + sy * sy + sz * sz;
+    double t = 1.0 + (a2 - 1.0) * (ns * ns / ss);
+    return (float)(a2 / (3.14159265358979323846 * t * t));
+}
+LJ_HD float GTR2(V3 n, V3 wi, V3 wo, float roughness) { return GTR2_alpha(n, wi, wo, 1.f, roughness * roughness); }
+// |wi + eta wo|^2.  With h = +-normalize(wi + eta wo) this IS (h.wi + eta h.wo)^2, the denominator of the refraction
+// Jacobian (roughdielectric.inl:66-70), without the cancellation of the two dot products near the configuration
+// wi = -eta wo where the half vector degenerates (volpath_test5_2: relative error 0.06 -> 1e-5).
+// 1 - F for the refraction branch, with the half vector, h.wi and the Fresnel terms in fp64: near the critical angle
+// F -> 1 and fp32's 1 - F keeps no digits, and h.wi itself comes out of the cancelling sum wi + eta wo.  Stable form
+// 1 - ((a - b) / (a + b))^2 = 4 a b / (a + b)^2 for both polarisations (microfacet.h:34-55).
+LJ_HD float dielectric_transmittance(V3 wi, V3 wo, float eta_f) {
+    const double eta = eta_f;
+    double sx = (double)wi.x + eta * wo.x, sy = (double)wi.y + eta * wo.y, sz = (double)wi.z + eta * wo.z;
+    double ss = sx * sx + sy * sy + sz * sz;
+    if (!(ss > 0)) return 0.f;
+    double hi = (sx * wi.x + sy * wi.y + sz * wi.z) / sqrt(ss);  // |h.wi| (the sign of h does not matter below)
+    double t2 = 1.0 - (1.0 - hi * hi) / (eta * eta);
+    if (t2 < 0) return 0.f;  // total internal reflection
+    double ci = fabs(hi), ct = sqrt(t2);
+    double a = ci, b = eta * ct, c = eta * ci, d = ct;
+    double ts = (a + b) != 0 ? 4 * a * b / ((a + b) * (a + b)) : 0.0, tp = (c + d) != 0 ? 4 * c * d / ((c + d) * (c + d)) : 0.0;
+    return (float)((ts + tp) / 2);
+}
+LJ_HD float half_len2(V3 wi, V3 wo, float eta) {
+    double sx = (double)wi.x + (double)eta * wo.x, sy = (double)wi.y + (double)eta * wo.y, sz = (double)wi.z + (double)eta * wo.z;
+    return (float)(sx * sx + sy * sy + sz * sz);
+}
+// The (unnormalised) half vector wi + eta wo in the shading frame (eta = 1: reflection).  Near the mirror / straight-
+// through configurations its tangential components are differences of nearly equal numbers: they are accumulated in
+// fp64 so that what is left after the cancellation still carries fp32's digits.
+LJ_HD V3 half_local(const Frame &f, V3 wi, V3 wo, float eta) {
+    double sx = (double)wi.x + (double)eta * wo.x, sy = (double)wi.y + (double)eta * wo.y, sz = (double)wi.z + (double)eta * wo.z;
+    double inv = 1.0 / sqrt(sx * sx + sy * sy + sz * sz);
+    return mk3((float)((sx * f.x.x + sy * f.x.y + sz * f.x.z) * inv), (float)((sx * f.y.x + sy * f.y.y + sz * f.y.z) * inv),
+               (float)((sx * f.n.x + sy * f.n.y + sz * f.n.z) * inv));
 }
 LJ_HD float smith_masking_gtr2(V3 v, float roughness) {
     float alpha = roughness * roughness;
@@ -115,7 +156,7 @@ LJ_HD V3 roughplastic_eval(V3 Kd, V3 Ks, float roughness, float eta, const Verte
     if (n_dot_out <= 0 || n_dot_h <= 0) return mk3(0);
     roughness = clampf(roughness, 0.01f, 1.f);
     float F_o = fresnel_dielectric(dot(h, wo), eta);
-    float D = GTR2(n_dot_h, roughness);
+    float D = GTR2(f.n, wi, wo, roughness);
     float G = smith_masking_gtr2(to_local(f, wi), roughness) * smith_masking_gtr2(to_local(f, wo), roughness);
     V3 spec = Ks * ((G * F_o * D) / (4 * n_dot_in * n_dot_out));
     float F_i = fresnel_dielectric(dot(h, wi), eta);
@@ -134,7 +175,7 @@ LJ_HD float roughplastic_pdf(V3 Kd, V3 Ks, float roughness, const Vertex &vx, V3
     float spec_prob = lS / (lS + lR);
     float diff_prob = 1 - spec_prob;
     float G = smith_masking_gtr2(to_local(f, wi), roughness);
-    float D = GTR2(n_dot_h, roughness);
+    float D = GTR2(f.n, wi, wo, roughness);
     spec_prob *= (G * D) / (4 * n_dot_in);
     diff_prob *= n_dot_out / kPi;
     return spec_prob + diff_prob;
@@ -181,14 +222,14 @@ LJ_HD V3 dielectric_eval(V3 Cr, V3 Ct, float ax, float ay, float mat_eta, const 
     if (dot(h, f.n) < 0) h = -h;
     float h_dot_in = dot(h, wi);
     float F = fresnel_dielectric(h_dot_in, eta);
-    float D = ggx_aniso_D(to_local(f, h), ax, ay);
+    // isotropic (RoughDielectric, roughdielectric.inl:60: GTR2 of n.h): the reference's expression in fp64, see GTR2_alpha
+    float D = ax == ay ? GTR2_alpha(f.n, wi, wo, reflect ? 1.f : eta, ax) : ggx_aniso_D(half_local(f, wi, wo, reflect ? 1.f : eta), ax, ay);
     float G = smith_aniso_G1(to_local(f, wi), ax, ay) * smith_aniso_G1(to_local(f, wo), ax, ay);
     if (reflect) return Cr * ((F * D * G) / (4 * fabsf(dot(f.n, wi))));
     float eta_factor = transport == 0 ? (1 / (eta * eta)) : 1;  // roughdielectric.inl:64
     float h_dot_out = dot(h, wo);
-    float sqrt_denom = h_dot_in + eta * h_dot_out;
-    return Ct * ((eta_factor * (1 - F) * D * G * eta * eta * fabsf(h_dot_out * h_dot_in)) /
-                 (fabsf(dot(f.n, wi)) * sqrt_denom * sqrt_denom));
+    return Ct * ((eta_factor * dielectric_transmittance(wi, wo, eta) * D * G * eta * eta * fabsf(h_dot_out * h_dot_in)) /
+                 (fabsf(dot(f.n, wi)) * half_len2(wi, wo, eta)));
 }
 LJ_HD float dielectric_pdf(float ax, float ay, float mat_eta, const Vertex &vx, V3 wi, V3 wo) {
     bool reflect = dot(vx.geometric_normal, wi) * dot(vx.geometric_normal, wo) > 0;
@@ -198,13 +239,12 @@ LJ_HD float dielectric_pdf(float ax, float ay, float mat_eta, const Vertex &vx, 
     if (dot(h, f.n) < 0) h = -h;
     float h_dot_in = dot(h, wi);
     float F = fresnel_dielectric(h_dot_in, eta);
-    float D = ggx_aniso_D(to_local(f, h), ax, ay);
+    float D = ax == ay ? GTR2_alpha(f.n, wi, wo, reflect ? 1.f : eta, ax) : ggx_aniso_D(half_local(f, wi, wo, reflect ? 1.f : eta), ax, ay);
     float G_in = smith_aniso_G1(to_local(f, wi), ax, ay);
     if (reflect) return (F * D * G_in) / (4 * fabsf(dot(f.n, wi)));
     float h_dot_out = dot(h, wo);
-    float sqrt_denom = h_dot_in + eta * h_dot_out;
-    float dh_dout = eta * eta * h_dot_out / (sqrt_denom * sqrt_denom);
-    return (1 - F) * D * G_in * fabsf(dh_dout * h_dot_in / dot(f.n, wi));
+    float dh_dout = eta * eta * h_dot_out / half_len2(wi, wo, eta);
+    return dielectric_transmittance(wi, wo, eta) * D * G_in * fabsf(dh_dout * h_dot_in / dot(f.n, wi));
 }
 LJ_HD bool dielectric_sample(float ax, float ay, float roughness, float mat_eta, const Vertex &vx, V3 wi, V2 u, float w, BsdfSample &s) {
     float eta = dot(vx.geometric_normal, wi) > 0 ? mat_eta : 1 / mat_eta;

@@ -193,7 +193,15 @@ def fixed_material_queries(n_materials):
     return q
 
 
-def check_bsdf_parity(scene, ref, q, med_tol=1e-5, max_tol=5e-3):
+def _tail_ok(e, med_tol, out, key):
+    """north_star's 1e-5 on the median; the fp32 tail characterised in profiles/r02_bsdf_tail.txt: at most 0.1 % of the
+    queries above 1e-4 (grazing directions and values 1e-6 of the peak), none above 2e-3."""
+    out[key + "_med"], out[key + "_max"] = float(np.median(e)), float(e.max())
+    out[key + "_gt1e4"] = float((e > 1e-4).mean())
+    assert np.median(e) <= med_tol and (e > 1e-4).mean() <= 1e-3 and e.max() <= 2e-3, out
+
+
+def check_bsdf_parity(scene, ref, q, med_tol=1e-5):
     r1, r2 = scene.bsdf(q), ref.bsdf(q)
     out = {}
     nz = (np.abs(r2["f"]).max(axis=1) > 1e-12)
@@ -203,13 +211,11 @@ def check_bsdf_parity(scene, ref, q, med_tol=1e-5, max_tol=5e-3):
     both = nz & z1
     if both.any():
         e = rel_err(r1["f"][both], r2["f"][both], 1e-9).max(axis=1)
-        out["f_med"], out["f_max"] = float(np.median(e)), float(e.max())
-        assert np.median(e) <= med_tol and np.quantile(e, 0.99) <= max_tol, out
+        _tail_ok(e, med_tol, out, "f")
     pz = (r2["pdf"] > 1e-12) & (r1["pdf"] > 1e-12)
     if pz.any():
         e = rel_err(r1["pdf"][pz], r2["pdf"][pz], 1e-9)
-        out["pdf_med"], out["pdf_max"] = float(np.median(e)), float(e.max())
-        assert np.median(e) <= med_tol and np.quantile(e, 0.99) <= max_tol, out
+        _tail_ok(e, med_tol, out, "pdf")
     assert (r1["sampled"] == r2["sampled"]).mean() > 0.999
     s = (r1["sampled"] == 1) & (r2["sampled"] == 1)
     # lobe selection (w < spec_prob, w <= F) can flip for a query within fp32 of the threshold
@@ -218,7 +224,7 @@ def check_bsdf_parity(scene, ref, q, med_tol=1e-5, max_tol=5e-3):
     if same_lobe.any():
         e = np.abs(r1["s_dir_out"][same_lobe].astype(np.float64) - r2["s_dir_out"][same_lobe]).max(axis=1)
         out["dir_med"], out["dir_max"] = float(np.median(e)), float(e.max())
-        assert np.median(e) <= med_tol and np.quantile(e, 0.99) <= max_tol, out
+        assert np.median(e) <= med_tol and np.quantile(e, 0.99) <= 5e-3, out
     return out
 
 
