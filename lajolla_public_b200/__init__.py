@@ -33,6 +33,8 @@ LIGHT_RESULT_DTYPE = np.dtype([("light_id", "<i4"), ("position", "<f4", 3), ("no
                                ("pdf", "<f4"), ("emission", "<f4", 3)])
 MEDIUM_QUERY_DTYPE = np.dtype([("org", "<f4", 3), ("tfar", "<f4"), ("dir", "<f4", 3), ("t", "<f4"), ("rnd", "<f4", 2),
                                ("medium_id", "<i4"), ("_pad", "<i4")])
+WALK_QUERY_DTYPE = np.dtype([("origin", "<f4", 3), ("medium_id", "<i4"), ("light_point", "<f4", 3), ("seed", "<u4"), ("c", "<f4", 3),
+                             ("pdf_nee", "<f4"), ("pdf_dir", "<f4"), ("budget", "<i4"), ("_pad", "<i4", 2)])
 MEDIUM_RESULT_DTYPE = np.dtype([("majorant", "<f4", 3), ("sigma_a", "<f4", 3), ("sigma_s", "<f4", 3), ("phase_dir", "<f4", 3),
                                 ("phase_eval", "<f4"), ("phase_pdf", "<f4")])
 
@@ -44,6 +46,7 @@ assert LIGHT_QUERY_DTYPE.itemsize == C.sizeof(abi.lj_light_query)
 assert LIGHT_RESULT_DTYPE.itemsize == C.sizeof(abi.lj_light_result)
 assert MEDIUM_QUERY_DTYPE.itemsize == C.sizeof(abi.lj_medium_query)
 assert MEDIUM_RESULT_DTYPE.itemsize == C.sizeof(abi.lj_medium_result)
+assert WALK_QUERY_DTYPE.itemsize == C.sizeof(abi.lj_walk_query)
 
 
 def _ptr(a, ctype):
@@ -164,6 +167,15 @@ class Scene:
         out = np.zeros(q.shape[0], dtype=MEDIUM_RESULT_DTYPE)
         abi.check(self._lib.lj_medium_batch(self._h, _ptr(q, abi.lj_medium_query), q.shape[0], _ptr(out, abi.lj_medium_result)))
         return out
+
+    def nee_walks(self, queries, kernel=abi.LJ_TRACE_PLAIN, pool_paths=0, slot_stride=1, want_ms=False):
+        """The volpath integrator's NEE walk for a batch of (origin, light point) queries: (n, 3) contributions."""
+        q = np.ascontiguousarray(queries, dtype=WALK_QUERY_DTYPE)
+        out = np.zeros((q.shape[0], 3), dtype=np.float32)
+        ms = C.c_double(0)
+        opts = abi.lj_trace_opts(kernel, pool_paths, slot_stride, 0)
+        abi.check(self._lib.lj_nee_walk_batch(self._h, _ptr(q, abi.lj_walk_query), q.shape[0], C.byref(opts), _ptr(out, C.c_float), C.byref(ms)))
+        return (out, ms.value) if want_ms else out
 
     def sample_primary(self, screen_pos):
         xy = np.ascontiguousarray(screen_pos, dtype=np.float32).reshape(-1, 2)

@@ -93,7 +93,12 @@ class lj_trace_opts(C.Structure):
     _fields_ = [("kernel", i32), ("pool_paths", i32), ("slot_stride", i32), ("_pad", i32)]
 
 
-LJ_TRACE_PLAIN, LJ_TRACE_WAVEFRONT, LJ_TRACE_WAVEFRONT_LANE = 0, 1, 2
+LJ_TRACE_PLAIN, LJ_TRACE_WAVEFRONT, LJ_TRACE_WAVEFRONT_LANE, LJ_TRACE_WALK_WHOLE, LJ_TRACE_WALK_STEP = 0, 1, 2, 3, 4
+
+
+class lj_walk_query(C.Structure):
+    _fields_ = [("origin", f32 * 3), ("medium_id", i32), ("light_point", f32 * 3), ("seed", u32), ("c", f32 * 3), ("pdf_nee", f32),
+                ("pdf_dir", f32), ("budget", i32), ("_pad", i32 * 2)]
 
 
 class lj_hit(C.Structure):
@@ -154,6 +159,7 @@ PROTOTYPES = {
     "lj_trace_any": (C.c_int, [C.c_void_p, C.POINTER(lj_ray), i64, C.POINTER(u8), C.POINTER(f64)]),
     "lj_trace_closest_ex": (C.c_int, [C.c_void_p, C.POINTER(lj_ray), i64, C.POINTER(lj_trace_opts), C.POINTER(lj_hit), C.POINTER(f64)]),
     "lj_trace_any_ex": (C.c_int, [C.c_void_p, C.POINTER(lj_ray), i64, C.POINTER(lj_trace_opts), C.POINTER(u8), C.POINTER(f64)]),
+    "lj_nee_walk_batch": (C.c_int, [C.c_void_p, C.POINTER(lj_walk_query), i64, C.POINTER(lj_trace_opts), pf32, C.POINTER(f64)]),
     "lj_intersect": (C.c_int, [C.c_void_p, C.POINTER(lj_ray), pf32, i64, C.POINTER(lj_vertex)]),
     "lj_bsdf_batch": (C.c_int, [C.c_void_p, C.POINTER(lj_bsdf_query), i64, C.POINTER(lj_bsdf_result)]),
     "lj_light_batch": (C.c_int, [C.c_void_p, C.POINTER(lj_light_query), i64, C.POINTER(lj_light_result)]),

@@ -200,6 +200,12 @@ struct NeeWalk {
     Pcg rng;
 };
 
+// The walk's own PCG stream: a function of the PATH (pixel * spp + sample) and of one draw of the path's stream,
+// never of the pool slot the path sits in -- renders are reproducible whatever the pool size or the split across GPUs.
+LJ_HD Pcg walk_rng(uint64_t path_id, uint32_t walk_seed, uint64_t seed) {
+    return pcg_init(path_stream(path_id) + (((uint64_t)walk_seed << 1) | 1ull), seed);
+}
+
 // tnear / tfar of the next segment
 LJ_HD void nee_walk_segment(const DevScene &sc, const NeeWalk &w, float &tnear, float &tfar) {
     tnear = sc.shadow_eps;

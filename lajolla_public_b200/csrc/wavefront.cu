@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(128, MODE >= 2 ? LJ_WALK_MIN_BLOCKS : (MODE ==
                         // whatever the pool size or the split across GPUs
                         {
                             const uint64_t path_id = (uint64_t)f2u(a.pool.meta[slot].x) * a.rp.spp_total + f2u(a.pool.aux[slot].z);
-                            wk.rng = pcg_init(path_stream(path_id) + (((uint64_t)f2u(pl.w) << 1) | 1ull), a.rp.seed);
+                            wk.rng = walk_rng(path_id, f2u(pl.w), a.rp.seed);
                         }
                         float tn;
                         nee_walk_segment(sc, wk, tn, seg_tfar);
@@ -1266,6 +1266,129 @@ static int trace_pool_impl(lj_scene *s, const lj_ray *rays, int64_t n, const lj_
     return LJ_OK;
 }
 
+// ---- the volpath NEE segment walk (homework2.tex:459-510, 771-810) through the persistent walk kernels, and as a plain
+// one-thread-per-walk loop over the same step functions: the two must agree bit for bit (same hits by the tie policy,
+// same PCG draws in the same order), which is what the parity test of k_trace<2> / k_trace<3> asserts.
+__global__ void __launch_bounds__(128) k_walk_plain(const LJ_GRID_CONSTANT DevScene sc, const lj_walk_query *q, int n, uint64_t seed, float *out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    lj_walk_query in = q[i];
+    NeeWalk wk;
+    wk.pc = mk3(in.origin[0], in.origin[1], in.origin[2]);
+    wk.pl = mk3(in.light_point[0], in.light_point[1], in.light_point[2]);
+    wk.dir = normalize(wk.pl - wk.pc);
+    wk.T_light = mk3(1); wk.p_nee = mk3(1); wk.p_dir = mk3(1);
+    wk.c = mk3(in.c[0], in.c[1], in.c[2]);
+    wk.pdf_nee = in.pdf_nee; wk.pdf_dir = in.pdf_dir;
+    wk.medium = in.medium_id;
+    wk.budget = in.budget < 0 ? kWalkNoBudget : (uint32_t)in.budget;
+    wk.shadow_bounces = 0;
+    wk.rng = walk_rng((uint64_t)i, in.seed, seed);
+    V3 contrib = mk3(0);
+    for (int guard = 0; guard < 1 << 16; guard++) {
+        float tn, tf;
+        nee_walk_segment(sc, wk, tn, tf);
+        Hit hit;
+        trace8<false>(sc.nodes8, sc.prims, wk.pc, wk.dir, tn, tf, hit);
+        float next_t = nee_walk_next_t(wk, hit);
+        if (wk.medium >= 0) ratio_track(sc.media[wk.medium], wk.pc, wk.dir, tf, next_t, sc.options.max_null_collisions, wk.rng, wk.T_light, wk.p_nee, wk.p_dir);
+        if (nee_walk_decide(sc, wk, hit, contrib)) break;
+    }
+    out[3 * i] = contrib.x; out[3 * i + 1] = contrib.y; out[3 * i + 2] = contrib.z;
+}
+__global__ void k_pool_load_walks(PathPool pool, const lj_walk_query *q, int m, int stride, int first) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool has = false;
+    if (i < pool.capacity) {
+        int k = i / stride;
+        has = (i % stride) == 0 && k < m;
+        V4 meta = mk4(0, 0, 0, 0), sh_d = mk4(0, 0, 0, -1.f);
+        if (has) {
+            lj_walk_query in = q[k];
+            V3 o = mk3(in.origin[0], in.origin[1], in.origin[2]), pl = mk3(in.light_point[0], in.light_point[1], in.light_point[2]);
+            V3 d = normalize(pl - o);
+            meta = mk4(u2f((uint32_t)(first + k)), u2f(1u | kOccupied), 0, 0);  // (pixel = walk index: the walk's RNG stream)
+            sh_d = mk4(d, in.pdf_dir);
+            uint32_t budget = in.budget < 0 ? kWalkNoBudget : (uint32_t)in.budget;
+            pool.sh_o[i] = mk4(o, u2f((uint32_t)((in.medium_id + 1) & 0xffff) | (budget << 16)));
+            pool.sh_pl[i] = mk4(pl, u2f(in.seed));
+            pool.sh_c[i] = mk4(in.c[0], in.c[1], in.c[2], in.pdf_nee);
+            pool.aux[i] = mk4(1, 0, u2f(0u), u2f((uint32_t)in.medium_id));
+        }
+        pool.meta[i] = meta;
+        pool.sh_d[i] = sh_d;
+        pool.rad[i] = mk4(0, 0, 0, 1.f);
+    }
+    unsigned mask = __ballot_sync(0xffffffffu, has);
+    if (LJ_LANE() == 0 && i < pool.capacity) pool.sh_mask[i / LJ_WARP_WIDTH] = mask;
+}
+__global__ void k_pool_store_walks(PathPool pool, int m, int stride, float *out) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= m) return;
+    V4 r = pool.rad[(size_t)k * stride];
+    out[3 * k] = r.x; out[3 * k + 1] = r.y; out[3 * k + 2] = r.z;
+}
+
+static int walk_batch_impl(lj_scene *s, const lj_walk_query *q, int64_t n, const lj_trace_opts *opts, float *out, double *kernel_ms) {
+    const int kernel = opts ? opts->kernel : LJ_TRACE_PLAIN;
+    const int stride = opts && opts->slot_stride > 1 ? opts->slot_stride : 1;
+    for (int64_t i = 0; i < n; i++)
+        if (q[i].medium_id < -1 || q[i].medium_id >= s->dev.num_media || q[i].budget >= (int)kWalkNoBudget) { set_error("walk query out of range"); return LJ_ERR_INVALID; }
+    if (n > (int64_t)1 << 30) { set_error("too many walks in one batch"); return LJ_ERR_INVALID; }
+    lj_walk_query *d_q = nullptr;
+    float *d_out = nullptr;
+    cudaStream_t stream = s->stream;
+    auto cleanup = [&]() { lj_dev_free(d_q); lj_dev_free(d_out); };
+    cudaError_t e = lj_dev_alloc((void **)&d_q, (size_t)n * sizeof(lj_walk_query));
+    if (e == cudaSuccess) e = lj_dev_alloc((void **)&d_out, (size_t)n * 3 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_q, q, (size_t)n * sizeof(lj_walk_query), cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) { cleanup(); return cuda_fail(e, "walk batch allocation"); }
+    double total_ms = 0;
+    if (kernel == LJ_TRACE_PLAIN) {
+        cudaEventRecord(s->ev[0], stream);
+        LJ_LAUNCH(k_walk_plain, (int)((n + 127) / 128), 128, stream, s->dev, d_q, (int)n, kPcgDefaultSeed, d_out);
+        cudaEventRecord(s->ev[1], stream);
+        e = cudaStreamSynchronize(stream);
+        float ms = 0;
+        if (e == cudaSuccess) { cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]); total_ms = ms; }
+    } else {
+        long long capacity = opts->pool_paths > 0 ? opts->pool_paths : std::min<long long>((long long)n * stride, 1 << 22);
+        capacity = std::max<long long>(1024, (capacity + 255) / 256 * 256);
+        const int per_round = (int)((capacity + stride - 1) / stride);
+        int r = ensure_pool(s, (int)capacity, true);
+        if (r == LJ_OK) r = ensure_render_buffers(s, s->dev.camera.width * s->dev.camera.height, false);
+        if (r != LJ_OK) { cleanup(); return r; }
+        WaveArgs a;
+        memset(&a, 0, sizeof(a));
+        a.pool = s->pool;
+        a.rp.spp_total = 1;
+        a.rp.seed = kPcgDefaultSeed;
+        fill_trace_args(s, a);
+        const int nb256 = ((int)capacity + 255) / 256;
+        for (int64_t done = 0; done < n && e == cudaSuccess; done += per_round) {
+            const int m = (int)std::min<int64_t>(per_round, n - done);
+            LJ_LAUNCH(k_pool_load_walks, nb256, 256, stream, s->pool, d_q + done, m, stride, (int)done);
+            cudaMemsetAsync(s->d_cursors, 0, 4 * sizeof(unsigned int), stream);
+            cudaMemsetAsync(s->d_counters, 0, sizeof(unsigned long long) * C_TOTAL, stream);
+            cudaEventRecord(s->ev[0], stream);
+            if (kernel == LJ_TRACE_WALK_STEP) LJ_LAUNCH(k_trace<3>, s->geom.step_blocks, 128, stream, s->dev, a);
+            else LJ_LAUNCH(k_trace<2>, s->geom.walk_blocks, 128, stream, s->dev, a);
+            cudaEventRecord(s->ev[1], stream);
+            LJ_LAUNCH(k_pool_store_walks, (m + 255) / 256, 256, stream, s->pool, m, stride, d_out + 3 * done);
+            e = cudaStreamSynchronize(stream);
+            if (e == cudaSuccess) e = cudaGetLastError();
+            float ms = 0;
+            if (e == cudaSuccess) { cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]); total_ms += ms; }
+        }
+    }
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpy(out, d_out, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost);
+    cleanup();
+    if (e != cudaSuccess) return cuda_fail(e, "walk batch");
+    if (kernel_ms) *kernel_ms = total_ms;
+    return LJ_OK;
+}
+
 }  // namespace lj
 
 using namespace lj;
@@ -1286,6 +1409,14 @@ extern "C" int lj_trace_any_ex(lj_scene *s, const lj_ray *rays, int64_t n, const
     if (n == 0) return LJ_OK;
     DeviceGuard guard(s->device);
     return trace_pool_impl(s, rays, n, opts, nullptr, occluded, kernel_ms);
+}
+
+extern "C" int lj_nee_walk_batch(lj_scene *s, const lj_walk_query *q, int64_t n, const lj_trace_opts *opts, float *contribution_rgb, double *kernel_ms) {
+    if (!s || !q || !contribution_rgb || n < 0) { set_error("invalid argument"); return LJ_ERR_INVALID; }
+    if (opts && opts->kernel != LJ_TRACE_PLAIN && opts->kernel != LJ_TRACE_WALK_WHOLE && opts->kernel != LJ_TRACE_WALK_STEP) { set_error("unknown walk kernel"); return LJ_ERR_INVALID; }
+    if (n == 0) return LJ_OK;
+    DeviceGuard guard(s->device);
+    return walk_batch_impl(s, q, n, opts, contribution_rgb, kernel_ms);
 }
 
 extern "C" int lj_render_device(lj_scene *s, const lj_render_opts *opts, float *d_out_rgb, void *stream, lj_stats *stats) {

@@ -98,6 +98,46 @@ def check_wavefront_trace(scene, ref, rays, shadow, configs, min_agree=0.9999):
     return out
 
 
+def make_walk_queries(scene, ref, n, seed=12):
+    """NEE walks as the volpath integrator issues them: from points inside the scene's media (and from surface points)
+    towards sampled light points, with random budgets."""
+    rng = np.random.default_rng(seed)
+    info = scene.info()
+    lo, hi = np.array(info.bounds_lo), np.array(info.bounds_hi)
+    origin = (lo + rng.random((n, 3)) * (hi - lo)).astype(np.float32)
+    lq = np.zeros(n, dtype=lj.LIGHT_QUERY_DTYPE)
+    lq["ref_point"] = origin
+    lq["rnd_uv"] = rng.random((n, 2))
+    lq["rnd_w"] = rng.random(n)
+    lq["light_w"] = rng.random(n)
+    ls = ref.sample_lights(lq)
+    q = np.zeros(n, dtype=lj.WALK_QUERY_DTYPE)
+    q["origin"] = origin
+    q["light_point"] = ls["position"]
+    n_media = len(scene.desc.media)
+    q["medium_id"] = rng.integers(-1, max(n_media, 1), size=n) if n_media else -1
+    q["seed"] = rng.integers(0, 2 ** 32, size=n, dtype=np.uint64).astype(np.uint32)
+    q["c"] = rng.random((n, 3)) + 0.1
+    q["pdf_nee"] = rng.random(n) + 0.05
+    q["pdf_dir"] = rng.random(n) * 2
+    q["budget"] = np.where(rng.random(n) < 0.3, rng.integers(0, 4, size=n), -1)
+    return q
+
+
+def check_walk_parity(scene, ref, n, configs):
+    """k_trace<2> / k_trace<3> (the persistent NEE-walk kernels: closest-hit segment -> ratio tracking -> index-matched
+    test -> next segment, walks handed to lanes through the sh_mask bit words) against the plain one-thread-per-walk
+    loop over the same step functions: bit-identical contributions for every pool shape."""
+    q = make_walk_queries(scene, ref, n)
+    base = scene.nee_walks(q)
+    assert np.all(np.isfinite(base))
+    for kernel, pool, stride in configs:
+        got = scene.nee_walks(q, kernel=kernel, pool_paths=pool, slot_stride=stride)
+        bad = got.view(np.uint32) != base.view(np.uint32)
+        assert not bad.any(), f"walk kernel {kernel} pool {pool} stride {stride}: {int(bad.any(axis=1).sum())} of {n} walks differ, e.g. {got[bad.any(axis=1)][:2]} vs {base[bad.any(axis=1)][:2]}"
+    return dict(n=int(n), unblocked=float((np.abs(base).max(axis=1) > 0).mean()), mean=float(base.mean()), configs=len(configs))
+
+
 def shadow_rays(ref, rays, seed=3):
     """Segments from hit points towards sampled light points, as path_tracing.h:124-128 builds them."""
     rng = np.random.default_rng(seed)

@@ -93,6 +93,17 @@ def test_pixel_filters(oracle, name):
         assert np.abs(blur(img) - blur(ref_img)).mean() <= np.abs(blur(img) - blur(g_img)).mean() + 1e-4
 
 
+@pytest.mark.parametrize("name", ["volpath_test6", "vol_cbox_teapot", "hetvol", "hetvol_colored"])
+def test_walk_kernels_parity(oracle, name):
+    """The volpath NEE-walk kernels k_trace<2> (whole tracking loops) and k_trace<3> (one collision per pass, traversal
+    and tracking phases voted per warp) against the serial walk, bit for bit, with full, sparse and multi-round pools."""
+    from lajolla_public_b200 import abi
+    sc, ref = pair(oracle, name)
+    W, S = abi.LJ_TRACE_WALK_WHOLE, abi.LJ_TRACE_WALK_STEP
+    cfg = [(W, 0, 1), (W, 0, 7), (W, 20000, 1), (S, 0, 1), (S, 0, 37), (S, 30000, 3), (S, 1000, 1)]
+    record("walk_parity", dict(scene=name, **pc.check_walk_parity(sc, ref, 1 << 16, cfg)))
+
+
 @pytest.mark.parametrize("name", SCENES)
 def test_vertex_camera_light_parity(oracle, name):
     sc, ref = pair(oracle, name)

@@ -66,6 +66,15 @@ def test_wavefront_kernels_ray_parity(oracle):
     pc.check_wavefront_trace(sc, ref, pc.shadow_rays(ref, rays), True, cfg)
 
 
+@pytest.mark.parametrize("name", ["volpath_test6", "hetvol"])
+def test_walk_kernels_parity(oracle, name):
+    from lajolla_public_b200 import abi
+    sc, ref = pair(oracle, name)
+    W, S = abi.LJ_TRACE_WALK_WHOLE, abi.LJ_TRACE_WALK_STEP
+    r = pc.check_walk_parity(sc, ref, 600 if name == "hetvol" else 2000, [(W, 0, 1), (S, 0, 1), (S, 1000, 3)])
+    assert r["unblocked"] > 0.05
+
+
 @pytest.mark.parametrize("name", SCENES)
 def test_vertex_camera_light_parity(oracle, name):
     sc, ref = pair(oracle, name)
