@@ -43,48 +43,50 @@ LJ_HD float fresnel_dielectric(float n_dot_i, float eta) {
 // the half vector is near the normal and alpha is small (veach_mi's alpha = 0.005: a2 = 2.5e-5); a cancellation-free
 // rewrite (sin^2 + a2 cos^2 from the tangential components) is NOT equivalent either, because the fp32 frame the
 // reference is handed is unit / orthogonal only to 1e-7 and its formula sees |n|^2 - 1 at full weight (relative
-// 4e-4 on D at n.h = 0.9998, profiles/r02_bsdf_tail.txt).  So the reference's own expression is evaluated, with the
-// half vector and n.h in fp64 (about a dozen DFMAs and one division per evaluation).
-// (half vector wi + eta wo: eta = 1 for reflection, the relative IOR for refraction, roughdielectric.inl:33-40)
+// 4e-4 on D at n.h = 0.9998, profiles/r02_bsdf_tail.txt).  So the reference's own expression is evaluated:
+// 1 + (a2 - 1) (n.h)^2 = ((s.s - (n.s)^2) + a2 (n.s)^2) / s.s with s = wi + eta wo (eta = 1 for reflection, the relative
+// IOR for refraction, roughdielectric.inl:33-40); the numerator's cancellation is done in fp64 (a dozen DFMAs), the
+// quotient in fp32 -- no fp64 division.
 LJ_HD float GTR2_alpha(V3 n, V3 wi, V3 wo, float eta, float alpha) {
     double a2 = (double)alpha * (double)alpha;
     double sx = (double)wi.x + (double)eta * wo.x, sy = (double)wi.y + (double)eta * wo.y, sz = (double)wi.z + (double)eta * wo.z;
     double ns = sx * n.x + sy * n.y + sz * n.z, ss = sx * sx + sy * sy + sz * sz;
-    double t = 1.0 + (a2 - 1.0) * (ns * ns / ss);
-    return (float)(a2 / (3.14159265358979323846 * t * t));
+    float t = (float)((ss - ns * ns) + a2 * (ns * ns)) / (float)ss;
+    return (float)a2 / (kPi * t * t);
 }
 LJ_HD float GTR2(V3 n, V3 wi, V3 wo, float roughness) { return GTR2_alpha(n, wi, wo, 1.f, roughness * roughness); }
+// 1 - F for the refraction branch.  Near the critical angle F -> 1 and fp32's 1 - F keeps no digits, and h.wi itself comes
+// out of the cancelling sum s = wi + eta wo.  The two delicate quantities are quotients whose numerators are formed in
+// fp64: cos^2 of the incident angle (s.wi)^2 / s.s, and of the transmitted angle (eta^2 s.s - (s.s - (s.wi)^2)) /
+// (eta^2 s.s); the rest is fp32, in the stable product form 1 - ((a - b) / (a + b))^2 = 4 a b / (a + b)^2 for both
+// polarisations (microfacet.h:34-55).  (volpath_test5_2: relative error 0.06 -> 1.5e-4.)
+LJ_HD float dielectric_transmittance(V3 wi, V3 wo, float eta) {
+    double sx = (double)wi.x + (double)eta * wo.x, sy = (double)wi.y + (double)eta * wo.y, sz = (double)wi.z + (double)eta * wo.z;
+    double ss = sx * sx + sy * sy + sz * sz, sw = sx * wi.x + sy * wi.y + sz * wi.z;
+    double e2 = (double)eta * (double)eta;
+    float ssf = (float)ss;
+    if (!(ssf > 0)) return 0.f;
+    float ci2 = (float)(sw * sw) / ssf;
+    float ct2 = (float)(e2 * ss - (ss - sw * sw)) / ((float)e2 * ssf);
+    if (ct2 < 0) return 0.f;  // total internal reflection
+    float ci = sqrtf(ci2), ct = sqrtf(ct2);
+    float a = ci, b = eta * ct, c = eta * ci, d = ct;
+    float ts = (a + b) != 0 ? 4 * a * b / ((a + b) * (a + b)) : 0.f, tp = (c + d) != 0 ? 4 * c * d / ((c + d) * (c + d)) : 0.f;
+    return (ts + tp) / 2;
+}
 // |wi + eta wo|^2.  With h = +-normalize(wi + eta wo) this IS (h.wi + eta h.wo)^2, the denominator of the refraction
 // Jacobian (roughdielectric.inl:66-70), without the cancellation of the two dot products near the configuration
-// wi = -eta wo where the half vector degenerates (volpath_test5_2: relative error 0.06 -> 1e-5).
-// 1 - F for the refraction branch, with the half vector, h.wi and the Fresnel terms in fp64: near the critical angle
-// F -> 1 and fp32's 1 - F keeps no digits, and h.wi itself comes out of the cancelling sum wi + eta wo.  Stable form
-// 1 - ((a - b) / (a + b))^2 = 4 a b / (a + b)^2 for both polarisations (microfacet.h:34-55).
-LJ_HD float dielectric_transmittance(V3 wi, V3 wo, float eta_f) {
-    const double eta = eta_f;
-    double sx = (double)wi.x + eta * wo.x, sy = (double)wi.y + eta * wo.y, sz = (double)wi.z + eta * wo.z;
-    double ss = sx * sx + sy * sy + sz * sz;
-    if (!(ss > 0)) return 0.f;
-    double hi = (sx * wi.x + sy * wi.y + sz * wi.z) / sqrt(ss);  // |h.wi| (the sign of h does not matter below)
-    double t2 = 1.0 - (1.0 - hi * hi) / (eta * eta);
-    if (t2 < 0) return 0.f;  // total internal reflection
-    double ci = fabs(hi), ct = sqrt(t2);
-    double a = ci, b = eta * ct, c = eta * ci, d = ct;
-    double ts = (a + b) != 0 ? 4 * a * b / ((a + b) * (a + b)) : 0.0, tp = (c + d) != 0 ? 4 * c * d / ((c + d) * (c + d)) : 0.0;
-    return (float)((ts + tp) / 2);
-}
+// wi = -eta wo where the half vector degenerates.
 LJ_HD float half_len2(V3 wi, V3 wo, float eta) {
     double sx = (double)wi.x + (double)eta * wo.x, sy = (double)wi.y + (double)eta * wo.y, sz = (double)wi.z + (double)eta * wo.z;
     return (float)(sx * sx + sy * sy + sz * sz);
 }
-// The (unnormalised) half vector wi + eta wo in the shading frame (eta = 1: reflection).  Near the mirror / straight-
-// through configurations its tangential components are differences of nearly equal numbers: they are accumulated in
-// fp64 so that what is left after the cancellation still carries fp32's digits.
+// The (unnormalised) half vector wi + eta wo in the shading frame.  Near the mirror / straight-through configurations
+// its tangential components are differences of nearly equal numbers: they are accumulated in fp64 so that what is left
+// after the cancellation still carries fp32's digits.  ggx_aniso_D divides by the squared length.
 LJ_HD V3 half_local(const Frame &f, V3 wi, V3 wo, float eta) {
     double sx = (double)wi.x + (double)eta * wo.x, sy = (double)wi.y + (double)eta * wo.y, sz = (double)wi.z + (double)eta * wo.z;
-    double inv = 1.0 / sqrt(sx * sx + sy * sy + sz * sz);
-    return mk3((float)((sx * f.x.x + sy * f.x.y + sz * f.x.z) * inv), (float)((sx * f.y.x + sy * f.y.y + sz * f.y.z) * inv),
-               (float)((sx * f.n.x + sy * f.n.y + sz * f.n.z) * inv));
+    return mk3((float)(sx * f.x.x + sy * f.x.y + sz * f.x.z), (float)(sx * f.y.x + sy * f.y.y + sz * f.y.z), (float)(sx * f.n.x + sy * f.n.y + sz * f.n.z));
 }
 LJ_HD float smith_masking_gtr2(V3 v, float roughness) {
     float alpha = roughness * roughness;
@@ -205,8 +207,8 @@ LJ_HD bool roughplastic_sample(V3 Kd, V3 Ks, float roughness, const Vertex &vx, 
 // ===================================================== RoughDielectric (roughdielectric.inl)
 // Shared with DisneyGlass: Cr / Ct are the reflection / transmission tints, (ax, ay) the GGX
 // alphas, D and G evaluated by the anisotropic forms below (isotropic when ax == ay).
-LJ_HD float ggx_aniso_D(V3 hl, float ax, float ay) {  // homework1.tex:197-201
-    float t = hl.x * hl.x / (ax * ax) + hl.y * hl.y / (ay * ay) + hl.z * hl.z;
+LJ_HD float ggx_aniso_D(V3 hl, float ax, float ay) {  // homework1.tex:197-201; hl need not be normalised
+    float t = (hl.x * hl.x / (ax * ax) + hl.y * hl.y / (ay * ay) + hl.z * hl.z) / (hl.x * hl.x + hl.y * hl.y + hl.z * hl.z);
     return 1 / (kPi * ax * ay * t * t);
 }
 LJ_HD float smith_aniso_G1(V3 wl, float ax, float ay) {  // homework1.tex:213-220
@@ -472,85 +474,141 @@ LJ_HD bool disney_bsdf_sample(const DisneyParams &p, const Vertex &vx, V3 wi, V2
 }
 
 // material.cpp:90-123: the three entry points, switch instead of std::visit.
-LJ_HD V3 bsdf_eval(const DevScene &sc, const DevMaterial &m, V3 wi, V3 wo, const Vertex &vx, int transport) {
-    switch (m.type) {
-        case 0: return lambertian_eval(mat_tex3(sc, m, 0, vx), vx, wi, wo);
-        case 1: return roughplastic_eval(mat_tex3(sc, m, 0, vx), mat_tex3(sc, m, 1, vx), mat_tex1(sc, m, 2, vx), m.eta, vx, wi, wo);
-        case 2: {
-            float r = clampf(mat_tex1(sc, m, 2, vx), 0.01f, 1.f);
-            return dielectric_eval(mat_tex3(sc, m, 1, vx), mat_tex3(sc, m, 0, vx), r * r, r * r, m.eta, vx, wi, wo, transport);
+// CLASS selects which alternatives are compiled in: kMatAll, kMatSmall (Lambertian, RoughPlastic, RoughDielectric) or
+// kMatDisney (the six Disney alternatives).  Scenes with Disney materials shade in two passes, one kernel per class
+// (wavefront.cu): the Disney lobes are ~10x the code of the small materials, and a kernel that holds both spends its
+// time waiting for instructions (60 % of the stall samples "no instruction", profiles/r02g_disney_shade_ncu.txt).
+enum { kMatAll = 0, kMatSmall = 1, kMatDisney = 2 };
+LJ_HD bool material_is_disney(int type) { return type >= LJ_MAT_DISNEY_DIFFUSE; }
+
+// A material at one vertex.  For the principled BSDF the twelve parameter textures are evaluated ONCE here instead of
+// inside each of the five eval / pdf / sample calls of a shade step.
+struct MatCtx {
+    const DevMaterial *m;
+    DisneyParams dp;
+};
+template <int CLASS>
+LJ_HD MatCtx mat_ctx(const DevScene &sc, const DevMaterial &m, const Vertex &vx) {
+    MatCtx c;
+    c.m = &m;
+    if (CLASS != kMatSmall && m.type == LJ_MAT_DISNEY_BSDF) c.dp = disney_params(sc, m, vx);
+    return c;
+}
+
+template <int CLASS>
+LJ_HD V3 bsdf_eval(const DevScene &sc, const MatCtx &c, V3 wi, V3 wo, const Vertex &vx, int transport) {
+    const DevMaterial &m = *c.m;
+    if (CLASS != kMatDisney) {
+        switch (m.type) {
+            case 0: return lambertian_eval(mat_tex3(sc, m, 0, vx), vx, wi, wo);
+            case 1: return roughplastic_eval(mat_tex3(sc, m, 0, vx), mat_tex3(sc, m, 1, vx), mat_tex1(sc, m, 2, vx), m.eta, vx, wi, wo);
+            case 2: {
+                float r = clampf(mat_tex1(sc, m, 2, vx), 0.01f, 1.f);
+                return dielectric_eval(mat_tex3(sc, m, 1, vx), mat_tex3(sc, m, 0, vx), r * r, r * r, m.eta, vx, wi, wo, transport);
+            }
         }
-        case 3: return disney_diffuse_eval(mat_tex3(sc, m, 0, vx), clampf(mat_tex1(sc, m, 2, vx), 0.01f, 1.f), mat_tex1(sc, m, 1, vx), vx, wi, wo);
-        case 4: {
-            float ax, ay;
-            disney_alphas(clampf(mat_tex1(sc, m, 2, vx), 0.01f, 1.f), mat_tex1(sc, m, 3, vx), ax, ay);
-            return disney_metal_eval(mat_tex3(sc, m, 0, vx), ax, ay, vx, wi, wo);
+    }
+    if (CLASS != kMatSmall) {
+        switch (m.type) {
+            case 3: return disney_diffuse_eval(mat_tex3(sc, m, 0, vx), clampf(mat_tex1(sc, m, 2, vx), 0.01f, 1.f), mat_tex1(sc, m, 1, vx), vx, wi, wo);
+            case 4: {
+                float ax, ay;
+                disney_alphas(clampf(mat_tex1(sc, m, 2, vx), 0.01f, 1.f), mat_tex1(sc, m, 3, vx), ax, ay);
+                return disney_metal_eval(mat_tex3(sc, m, 0, vx), ax, ay, vx, wi, wo);
+            }
+            case 5: {
+                float ax, ay;
+                disney_alphas(clampf(mat_tex1(sc, m, 2, vx), 0.01f, 1.f), mat_tex1(sc, m, 3, vx), ax, ay);
+                V3 base = mat_tex3(sc, m, 0, vx);
+                return dielectric_eval(base, sqrt3(base), ax, ay, m.eta, vx, wi, wo, transport);
+            }
+            case 6: return mk3(disney_clearcoat_eval(mat_tex1(sc, m, 4, vx), vx, wi, wo));
+            case 7: return disney_sheen_eval(mat_tex3(sc, m, 0, vx), mat_tex1(sc, m, 5, vx), vx, wi, wo);
+            case 8: return disney_bsdf_eval(c.dp, vx, wi, wo, transport);
         }
-        case 5: {
-            float ax, ay;
-            disney_alphas(clampf(mat_tex1(sc, m, 2, vx), 0.01f, 1.f), mat_tex1(sc, m, 3, vx), ax, ay);
-            V3 base = mat_tex3(sc, m, 0, vx);
-            return dielectric_eval(base, sqrt3(base), ax, ay, m.eta, vx, wi, wo, transport);
-        }
-        case 6: return mk3(disney_clearcoat_eval(mat_tex1(sc, m, 4, vx), vx, wi, wo));
-        case 7: return disney_sheen_eval(mat_tex3(sc, m, 0, vx), mat_tex1(sc, m, 5, vx), vx, wi, wo);
-        case 8: return disney_bsdf_eval(disney_params(sc, m, vx), vx, wi, wo, transport);
     }
     return mk3(0);
 }
 
-LJ_HD float bsdf_pdf(const DevScene &sc, const DevMaterial &m, V3 wi, V3 wo, const Vertex &vx) {
-    switch (m.type) {
-        case 0: case 3: case 7: return lambertian_pdf(vx, wi, wo);
-        case 1: return roughplastic_pdf(mat_tex3(sc, m, 0, vx), mat_tex3(sc, m, 1, vx), mat_tex1(sc, m, 2, vx), vx, wi, wo);
-        case 2: {
-            float r = clampf(mat_tex1(sc, m, 2, vx), 0.01f, 1.f);
-            return dielectric_pdf(r * r, r * r, m.eta, vx, wi, wo);
+template <int CLASS>
+LJ_HD float bsdf_pdf(const DevScene &sc, const MatCtx &c, V3 wi, V3 wo, const Vertex &vx) {
+    const DevMaterial &m = *c.m;
+    if (CLASS != kMatDisney) {
+        switch (m.type) {
+            case 0: return lambertian_pdf(vx, wi, wo);
+            case 1: return roughplastic_pdf(mat_tex3(sc, m, 0, vx), mat_tex3(sc, m, 1, vx), mat_tex1(sc, m, 2, vx), vx, wi, wo);
+            case 2: {
+                float r = clampf(mat_tex1(sc, m, 2, vx), 0.01f, 1.f);
+                return dielectric_pdf(r * r, r * r, m.eta, vx, wi, wo);
+            }
         }
-        case 4: case 5: {
-            float ax, ay;
-            disney_alphas(clampf(mat_tex1(sc, m, 2, vx), 0.01f, 1.f), mat_tex1(sc, m, 3, vx), ax, ay);
-            return m.type == 4 ? disney_metal_pdf(ax, ay, vx, wi, wo) : dielectric_pdf(ax, ay, m.eta, vx, wi, wo);
+    }
+    if (CLASS != kMatSmall) {
+        switch (m.type) {
+            case 3: case 7: return lambertian_pdf(vx, wi, wo);
+            case 4: case 5: {
+                float ax, ay;
+                disney_alphas(clampf(mat_tex1(sc, m, 2, vx), 0.01f, 1.f), mat_tex1(sc, m, 3, vx), ax, ay);
+                return m.type == 4 ? disney_metal_pdf(ax, ay, vx, wi, wo) : dielectric_pdf(ax, ay, m.eta, vx, wi, wo);
+            }
+            case 6: return disney_clearcoat_pdf(mat_tex1(sc, m, 4, vx), vx, wi, wo);
+            case 8: return disney_bsdf_pdf(c.dp, vx, wi, wo);
         }
-        case 6: return disney_clearcoat_pdf(mat_tex1(sc, m, 4, vx), vx, wi, wo);
-        case 8: return disney_bsdf_pdf(disney_params(sc, m, vx), vx, wi, wo);
     }
     return 0;
 }
 
-LJ_HD bool bsdf_sample(const DevScene &sc, const DevMaterial &m, V3 wi, const Vertex &vx, V2 u, float w, BsdfSample &s) {
-    switch (m.type) {
-        case 0: case 3: case 7: return lambertian_sample(vx, wi, u, s);
-        case 1: return roughplastic_sample(mat_tex3(sc, m, 0, vx), mat_tex3(sc, m, 1, vx), mat_tex1(sc, m, 2, vx), vx, wi, u, w, s);
-        case 2: {
-            float r = clampf(mat_tex1(sc, m, 2, vx), 0.01f, 1.f);
-            return dielectric_sample(r * r, r * r, r, m.eta, vx, wi, u, w, s);
+template <int CLASS>
+LJ_HD bool bsdf_sample(const DevScene &sc, const MatCtx &c, V3 wi, const Vertex &vx, V2 u, float w, BsdfSample &s) {
+    const DevMaterial &m = *c.m;
+    if (CLASS != kMatDisney) {
+        switch (m.type) {
+            case 0: return lambertian_sample(vx, wi, u, s);
+            case 1: return roughplastic_sample(mat_tex3(sc, m, 0, vx), mat_tex3(sc, m, 1, vx), mat_tex1(sc, m, 2, vx), vx, wi, u, w, s);
+            case 2: {
+                float r = clampf(mat_tex1(sc, m, 2, vx), 0.01f, 1.f);
+                return dielectric_sample(r * r, r * r, r, m.eta, vx, wi, u, w, s);
+            }
         }
-        case 4: case 5: {
-            float r = clampf(mat_tex1(sc, m, 2, vx), 0.01f, 1.f);
-            float ax, ay;
-            disney_alphas(r, mat_tex1(sc, m, 3, vx), ax, ay);
-            if (m.type == 4) return disney_metal_sample(ax, ay, r, vx, wi, u, s);
-            return dielectric_sample(ax, ay, r, m.eta, vx, wi, u, w, s);
+    }
+    if (CLASS != kMatSmall) {
+        switch (m.type) {
+            case 3: case 7: return lambertian_sample(vx, wi, u, s);
+            case 4: case 5: {
+                float r = clampf(mat_tex1(sc, m, 2, vx), 0.01f, 1.f);
+                float ax, ay;
+                disney_alphas(r, mat_tex1(sc, m, 3, vx), ax, ay);
+                if (m.type == 4) return disney_metal_sample(ax, ay, r, vx, wi, u, s);
+                return dielectric_sample(ax, ay, r, m.eta, vx, wi, u, w, s);
+            }
+            case 6: return disney_clearcoat_sample(mat_tex1(sc, m, 4, vx), vx, wi, u, s);
+            case 8: return disney_bsdf_sample(c.dp, vx, wi, u, w, s);
         }
-        case 6: return disney_clearcoat_sample(mat_tex1(sc, m, 4, vx), vx, wi, u, s);
-        case 8: return disney_bsdf_sample(disney_params(sc, m, vx), vx, wi, u, w, s);
     }
     return false;
 }
 
-// Out-of-line copies of the three dispatchers (one per translation unit instead of one per call site) for scenes
-// with Disney materials: inlined five times, the Disney lobes made k_shade 1.5 MB of SASS and the kernel spent its
-// time waiting for instructions (8 % of issue slots used on disney_bsdf; shade stage 675 -> 561 ms with calls).
-// Scenes with the small materials only keep the inlined form, which is 5-15 % faster for them.
-LJ_HD_CALL V3 bsdf_eval_call(const DevScene &sc, const DevMaterial &m, V3 wi, V3 wo, const Vertex &vx, int transport) {
-    return bsdf_eval(sc, m, wi, wo, vx, transport);
+// The query seam and the volpath integrator take a material and evaluate everything (one context per call).
+LJ_HD V3 bsdf_eval(const DevScene &sc, const DevMaterial &m, V3 wi, V3 wo, const Vertex &vx, int transport) {
+    return bsdf_eval<kMatAll>(sc, mat_ctx<kMatAll>(sc, m, vx), wi, wo, vx, transport);
 }
-LJ_HD_CALL float bsdf_pdf_call(const DevScene &sc, const DevMaterial &m, V3 wi, V3 wo, const Vertex &vx) {
-    return bsdf_pdf(sc, m, wi, wo, vx);
+LJ_HD float bsdf_pdf(const DevScene &sc, const DevMaterial &m, V3 wi, V3 wo, const Vertex &vx) {
+    return bsdf_pdf<kMatAll>(sc, mat_ctx<kMatAll>(sc, m, vx), wi, wo, vx);
 }
-LJ_HD_CALL bool bsdf_sample_call(const DevScene &sc, const DevMaterial &m, V3 wi, const Vertex &vx, V2 u, float w, BsdfSample &s) {
-    return bsdf_sample(sc, m, wi, vx, u, w, s);
+LJ_HD bool bsdf_sample(const DevScene &sc, const DevMaterial &m, V3 wi, const Vertex &vx, V2 u, float w, BsdfSample &s) {
+    return bsdf_sample<kMatAll>(sc, mat_ctx<kMatAll>(sc, m, vx), wi, vx, u, w, s);
+}
+
+// Out-of-line copies of the Disney-class dispatchers (one per translation unit instead of one per call site): inlined
+// five times, the Disney lobes made the shade kernel 1.5 MB of SASS.
+LJ_HD_CALL V3 bsdf_eval_call(const DevScene &sc, const MatCtx &c, V3 wi, V3 wo, const Vertex &vx, int transport) {
+    return bsdf_eval<kMatDisney>(sc, c, wi, wo, vx, transport);
+}
+LJ_HD_CALL float bsdf_pdf_call(const DevScene &sc, const MatCtx &c, V3 wi, V3 wo, const Vertex &vx) {
+    return bsdf_pdf<kMatDisney>(sc, c, wi, wo, vx);
+}
+LJ_HD_CALL bool bsdf_sample_call(const DevScene &sc, const MatCtx &c, V3 wi, const Vertex &vx, V2 u, float w, BsdfSample &s) {
+    return bsdf_sample<kMatDisney>(sc, c, wi, vx, u, w, s);
 }
 
 }  // namespace lj

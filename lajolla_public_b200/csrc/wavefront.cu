@@ -649,25 +649,31 @@ __global__ void __launch_bounds__(kQWarps * LJ_WARP_WIDTH, 8) k_trace_q(const LJ
 }
 
 
-// K4
-template <int MIN_BLOCKS, bool CALLS>
-__global__ void __launch_bounds__(128, MIN_BLOCKS) k_shade(const LJ_GRID_CONSTANT DevScene sc, const LJ_GRID_CONSTANT WaveArgs a) {
+// K4.  CLASS = kMatSmall: the kernel every path-integrator scene runs; in a scene WITH Disney materials it skips the
+// paths whose vertex carries one, and a second pass (CLASS = kMatDisney) shades those: one kernel per material class
+// ("material-sorted" at kernel granularity -- the slots stay where they are, each pass touches the records of its own
+// class only).  The first pass writes the sh_mask words, the second ORs its bits in.
+template <int MIN_BLOCKS, int CLASS>
+__global__ void __launch_bounds__(128, MIN_BLOCKS) k_shade(const LJ_GRID_CONSTANT DevScene sc, const LJ_GRID_CONSTANT WaveArgs a, int split_classes) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     ShadeCounters cnt = {0, 0, 0, 0};
     bool has_shadow = false;
     if (i < a.pool.capacity) {
         uint32_t flags = f2u(a.pool.meta[i].y);
-        if (flags & kAlive) {
+        if ((flags & kAlive) && (!split_classes || path_material_class(sc, (int)f2u(a.pool.hit[i].w)) == CLASS)) {
             PathState s;
             load_state(a.pool, i, s);
-            shade_path<CALLS>(sc, a.rp, s, cnt);
+            shade_path<CLASS>(sc, a.rp, s, cnt);
             store_state(a.pool, i, s, (s.flags & kAlive) != 0);
             has_shadow = s.sh_tfar >= 0;
         }
     }
     {   // capacity is a multiple of 256 (render_impl): whole warps are in range
         unsigned m = __ballot_sync(0xffffffffu, has_shadow);
-        if (LJ_LANE() == 0 && i < a.pool.capacity) a.pool.sh_mask[i / LJ_WARP_WIDTH] = m;
+        if (LJ_LANE() == 0 && i < a.pool.capacity) {
+            if (CLASS == kMatDisney) { if (m) a.pool.sh_mask[i / LJ_WARP_WIDTH] |= m; }
+            else a.pool.sh_mask[i / LJ_WARP_WIDTH] = m;
+        }
     }
     warp_add(&a.counters[C_BOUNCES_STRIPED + ((blockIdx.x * 4 + (threadIdx.x >> 5)) & (kStripes - 1))], cnt.bounces);
 }
@@ -1093,10 +1099,11 @@ static int render_impl(lj_scene *s, const lj_render_opts *opts_in, float *d_out,
         if (vol) {
             if (sc.num_media > 0) { LJ_LAUNCH(k_flight, g.flight_blocks, 128, stream, sc, a); launches++; }
             LJ_LAUNCH(k_shade_vol, nb128, 128, stream, sc, a);
-        } else if (s->has_disney) {
-            LJ_LAUNCH((k_shade<4, true>), nb128, 128, stream, sc, a);
         } else {
-            LJ_LAUNCH((k_shade<4, false>), nb128, 128, stream, sc, a);
+            // one pass per material class; the classes are disjoint and a path's class is read from its hit record,
+            // which the shade passes do not modify: every live path is shaded exactly once per wave
+            LJ_LAUNCH((k_shade<4, kMatSmall>), nb128, 128, stream, sc, a, s->has_disney ? 1 : 0);
+            if (s->has_disney) { LJ_LAUNCH((k_shade<4, kMatDisney>), nb128, 128, stream, sc, a, 1); launches++; }
         }
         LJ_CUDA(cudaEventRecord(e3, stream));
         if (vol && s->has_grid_media) LJ_LAUNCH(k_trace<3>, g.step_blocks, 128, stream, sc, a);
