@@ -49,9 +49,9 @@ def workload_name(key, w, h, full_spp):
     return f"{key} {w}x{h} {'volpath' if key in VOLPATH else 'path'} integrator, {full_spp} spp"
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_trace<0> launch (3.9 M rays) from the ncu --set full capture
-# profiles/r01n_sponza_ncu.txt (sponza, steady-state wave); other workloads have no capture of that kernel
-NCU_TRAFFIC_BYTES_PER_LAUNCH = {"sponza": 213.118720e6 + 57.262592e6}
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_trace_q<0> launch (3.9 M rays) from the ncu --set full capture
+# profiles/r02b_sponza_ncu.txt (sponza, steady-state wave); other workloads have no capture of that kernel
+NCU_TRAFFIC_BYTES_PER_LAUNCH = {"sponza": 217.652480e6 + 48.599808e6}
 
 
 def load_peaks():
@@ -325,13 +325,13 @@ def main():
             "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": int(cdesc_bytes),
                     "d2h_bytes_per_step": int(npix * 3 * 4), "includes": "lj_scene_create (upload + GPU BVH/mip build) + lj_render + D2H", "parts": e2e_parts},
             "gpu_launches": int(agg["launches"]),
-            "roofline": {"bound": "hbm", "kernel": "k_trace<0> (closest-hit extension)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_trace_q<0> (closest-hit extension)" if key not in VOLPATH else "k_trace<0> (closest-hit extension)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH.get(key) if spp == full_spp else None,
-                         "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r01n_sponza_ncu.txt)", "peak_kind": peak_kind,
+                         "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r02b_sponza_ncu.txt)", "peak_kind": peak_kind,
                          "algorithmic_bytes_per_ray": BYTES_PER_EXTENSION_RAY,
                          "rays_per_launch": agg["closest"] / max(agg["extend_launches"], 1),
                          "avg_launch_ms": agg["extend_ms"] / max(agg["extend_launches"], 1)},
-            "roofline_l2": {"bound": "l2", "kernel": "k_trace<0> + k_trace<1|2|3>", "unit": "GB/s", "peak": l2_peak,
+            "roofline_l2": {"bound": "l2", "kernel": "k_trace_q<0|1> (path) / k_trace<0|2|3> (volpath)", "unit": "GB/s", "peak": l2_peak,
                             "peak_kind": "measured here: read-only 16-byte-load stream over a 32 MB working set, all SMs (lj_measure_read_bandwidth)",
                             "hbm_read_gbs_same_probe": hbm_read,
                             "achieved": (agg["node_steps"] * 80 + agg["prim_tests"] * 48) / max((agg["extend_ms"] + agg["shadow_ms"]) / 1e3, 1e-9) / 1e9,

@@ -47,14 +47,20 @@ LJ_HD float fresnel_dielectric(float n_dot_i, float eta) {
 // 1 + (a2 - 1) (n.h)^2 = ((s.s - (n.s)^2) + a2 (n.s)^2) / s.s with s = wi + eta wo (eta = 1 for reflection, the relative
 // IOR for refraction, roughdielectric.inl:33-40); the numerator's cancellation is done in fp64 (a dozen DFMAs), the
 // quotient in fp32 -- no fp64 division.
-LJ_HD float GTR2_alpha(V3 n, V3 wi, V3 wo, float eta, float alpha) {
+// `ndh` is the caller's fp32 n.h: where the fp32 denominator is not small (t >= 0.05: relative error <= 5e-6) it is
+// used as it is, and the fp64 path only runs for the near-specular configurations that need it.
+LJ_HD float GTR2_alpha(V3 n, V3 wi, V3 wo, float eta, float alpha, float ndh) {
+    {
+        float a2f = alpha * alpha, tf = 1 + (a2f - 1) * ndh * ndh;
+        if (tf >= 0.05f) return a2f / (kPi * tf * tf);
+    }
     double a2 = (double)alpha * (double)alpha;
     double sx = (double)wi.x + (double)eta * wo.x, sy = (double)wi.y + (double)eta * wo.y, sz = (double)wi.z + (double)eta * wo.z;
     double ns = sx * n.x + sy * n.y + sz * n.z, ss = sx * sx + sy * sy + sz * sz;
     float t = (float)((ss - ns * ns) + a2 * (ns * ns)) / (float)ss;
     return (float)a2 / (kPi * t * t);
 }
-LJ_HD float GTR2(V3 n, V3 wi, V3 wo, float roughness) { return GTR2_alpha(n, wi, wo, 1.f, roughness * roughness); }
+LJ_HD float GTR2(V3 n, V3 wi, V3 wo, float roughness, float ndh) { return GTR2_alpha(n, wi, wo, 1.f, roughness * roughness, ndh); }
 // 1 - F for the refraction branch.  Near the critical angle F -> 1 and fp32's 1 - F keeps no digits, and h.wi itself comes
 // out of the cancelling sum s = wi + eta wo.  The two delicate quantities are quotients whose numerators are formed in
 // fp64: cos^2 of the incident angle (s.wi)^2 / s.s, and of the transmitted angle (eta^2 s.s - (s.s - (s.wi)^2)) /
@@ -158,7 +164,7 @@ LJ_HD V3 roughplastic_eval(V3 Kd, V3 Ks, float roughness, float eta, const Verte
     if (n_dot_out <= 0 || n_dot_h <= 0) return mk3(0);
     roughness = clampf(roughness, 0.01f, 1.f);
     float F_o = fresnel_dielectric(dot(h, wo), eta);
-    float D = GTR2(f.n, wi, wo, roughness);
+    float D = GTR2(f.n, wi, wo, roughness, n_dot_h);
     float G = smith_masking_gtr2(to_local(f, wi), roughness) * smith_masking_gtr2(to_local(f, wo), roughness);
     V3 spec = Ks * ((G * F_o * D) / (4 * n_dot_in * n_dot_out));
     float F_i = fresnel_dielectric(dot(h, wi), eta);
@@ -177,7 +183,7 @@ LJ_HD float roughplastic_pdf(V3 Kd, V3 Ks, float roughness, const Vertex &vx, V3
     float spec_prob = lS / (lS + lR);
     float diff_prob = 1 - spec_prob;
     float G = smith_masking_gtr2(to_local(f, wi), roughness);
-    float D = GTR2(f.n, wi, wo, roughness);
+    float D = GTR2(f.n, wi, wo, roughness, n_dot_h);
     spec_prob *= (G * D) / (4 * n_dot_in);
     diff_prob *= n_dot_out / kPi;
     return spec_prob + diff_prob;
@@ -225,7 +231,7 @@ LJ_HD V3 dielectric_eval(V3 Cr, V3 Ct, float ax, float ay, float mat_eta, const 
     float h_dot_in = dot(h, wi);
     float F = fresnel_dielectric(h_dot_in, eta);
     // isotropic (RoughDielectric, roughdielectric.inl:60: GTR2 of n.h): the reference's expression in fp64, see GTR2_alpha
-    float D = ax == ay ? GTR2_alpha(f.n, wi, wo, reflect ? 1.f : eta, ax) : ggx_aniso_D(half_local(f, wi, wo, reflect ? 1.f : eta), ax, ay);
+    float D = ax == ay ? GTR2_alpha(f.n, wi, wo, reflect ? 1.f : eta, ax, dot(f.n, h)) : ggx_aniso_D(half_local(f, wi, wo, reflect ? 1.f : eta), ax, ay);
     float G = smith_aniso_G1(to_local(f, wi), ax, ay) * smith_aniso_G1(to_local(f, wo), ax, ay);
     if (reflect) return Cr * ((F * D * G) / (4 * fabsf(dot(f.n, wi))));
     float eta_factor = transport == 0 ? (1 / (eta * eta)) : 1;  // roughdielectric.inl:64
@@ -241,7 +247,7 @@ LJ_HD float dielectric_pdf(float ax, float ay, float mat_eta, const Vertex &vx, 
     if (dot(h, f.n) < 0) h = -h;
     float h_dot_in = dot(h, wi);
     float F = fresnel_dielectric(h_dot_in, eta);
-    float D = ax == ay ? GTR2_alpha(f.n, wi, wo, reflect ? 1.f : eta, ax) : ggx_aniso_D(half_local(f, wi, wo, reflect ? 1.f : eta), ax, ay);
+    float D = ax == ay ? GTR2_alpha(f.n, wi, wo, reflect ? 1.f : eta, ax, dot(f.n, h)) : ggx_aniso_D(half_local(f, wi, wo, reflect ? 1.f : eta), ax, ay);
     float G_in = smith_aniso_G1(to_local(f, wi), ax, ay);
     if (reflect) return (F * D * G_in) / (4 * fabsf(dot(f.n, wi)));
     float h_dot_out = dot(h, wo);
