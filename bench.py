@@ -174,7 +174,7 @@ def main():
     ap.add_argument("--pool", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
-    ap.add_argument("--split", default="spp", choices=["spp", "tiles"])
+    ap.add_argument("--split", default="tiles", choices=["spp", "tiles"])
     ap.add_argument("--backend", default="nccl", choices=["nccl", "gloo"], help="diagnostic: gloo reduces the film through host memory")
     ap.add_argument("--no-reduce", action="store_true", help="diagnostic: skip the film reduction (the image stays split across ranks)")
     args = ap.parse_args()

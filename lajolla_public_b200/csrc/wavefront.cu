@@ -589,15 +589,17 @@ __global__ void __launch_bounds__(kQWarps * LJ_WARP_WIDTH, 8) k_trace_q(const LJ
             prim_passes += kind == Q_PRIM;
             bool finished = false;
             if (lane < nsel) {
+                // (each kind of step reads and writes only the fields it needs: the kernel is bound by the shared-memory /
+                //  L1 data pipe, profiles/r02b_sponza_ncu.txt)
                 const int r = (int)q.list[lane];
                 Trav tr;
                 tr.o = mk3(q.ox[r], q.oy[r], q.oz[r]);
                 tr.d = mk3(q.dx[r], q.dy[r], q.dz[r]);
                 tr.hit.t = q.tfar[r];
-                tr.hit.prim = q.prim[r];
                 tr.hit.u = tr.hit.v = 0;
                 if (kind == Q_FIN) {
                     const int slot = q.slot[r];
+                    tr.hit.prim = q.prim[r];
                     if (SHADOW) {
                         if (tr.hit.prim == kNoHit) {
                             V4 rd = a.pool.rad[slot], c = a.pool.sh_c[slot];
@@ -610,30 +612,49 @@ __global__ void __launch_bounds__(kQWarps * LJ_WARP_WIDTH, 8) k_trace_q(const LJ
                     q.status[r] = Q_EMPTY;
                 } else {
                     tr.tnear = q.tnear[r];
-                    tr.G.x = q.Gx[r]; tr.G.y = q.Gy[r];
-                    tr.sp = (int)q.sp[r];
+                    const int sp0 = (int)q.sp[r];
+                    tr.sp = sp0;
                     StridedStack stk;
                     stk.base = stack_base + r;
                     stk.stride = kQRays;
                     if (kind == Q_NODE) {
+                        tr.G.x = q.Gx[r]; tr.G.y = q.Gy[r];
+                        tr.hit.prim = kNoHit;  // (not read by a node step)
                         tr.idir = trav_idir_fast(tr.d);
                         const uint32_t oct = (tr.d.x < 0 ? 1u : 0u) | (tr.d.y < 0 ? 2u : 0u) | (tr.d.z < 0 ? 4u : 0u);
                         tr.octinv4 = (7u ^ oct) * 0x01010101u;
                         node_steps++;
                         trav_node(sc.nodes8, tr, stk, a.one_bits);
+                        trav_next_group(tr, stk);
+                        q.Gx[r] = tr.G.x; q.Gy[r] = tr.G.y; q.Tx[r] = tr.Gt.x; q.Ty[r] = tr.Gt.y;
+                        if (tr.sp != sp0) q.sp[r] = (uint32_t)tr.sp;
+                        const uint32_t st = q_status_of(tr);
+                        if (st != (uint32_t)Q_NODE) q.status[r] = st;
+                        finished = st == Q_FIN;
                     } else {
+                        const float t0 = tr.hit.t;
+                        const int p0 = q.prim[r];
+                        tr.hit.prim = p0;
+                        tr.G.x = 0; tr.G.y = q.Gy[r];  // (G.x is only needed once the group is entered: it stays in the table)
                         tr.Gt.x = q.Tx[r]; tr.Gt.y = q.Ty[r];
                         prim_tests++;
-                        if (trav_prim<SHADOW>(sc.prims, tr)) trav_terminate(tr);  // any-hit ends at the first hit
-                        q.tfar[r] = tr.hit.t;
-                        q.prim[r] = tr.hit.prim;
+                        const bool ended = trav_prim<SHADOW>(sc.prims, tr);  // any-hit ends at the first hit
+                        if (ended) trav_terminate(tr);
+                        if (tr.hit.t != t0 || tr.hit.prim != p0) { q.tfar[r] = tr.hit.t; q.prim[r] = tr.hit.prim; }
+                        const bool pop = !ended && (tr.G.y | tr.Gt.y) == 0 && tr.sp > 0;
+                        if (pop) {
+                            tr.G.x = q.Gx[r];  // (a popped primitive group leaves G as it was: empty)
+                            trav_next_group(tr, stk);
+                            q.Gx[r] = tr.G.x; q.Gy[r] = tr.G.y; q.Tx[r] = tr.Gt.x; q.Ty[r] = tr.Gt.y;
+                            q.sp[r] = (uint32_t)tr.sp;
+                        } else {
+                            q.Ty[r] = tr.Gt.y;
+                            if (ended) { q.Gy[r] = 0; q.sp[r] = 0; }
+                        }
+                        const uint32_t st = q_status_of(tr);
+                        if (st != (uint32_t)Q_PRIM) q.status[r] = st;
+                        finished = st == Q_FIN;
                     }
-                    trav_next_group(tr, stk);
-                    q.Gx[r] = tr.G.x; q.Gy[r] = tr.G.y; q.Tx[r] = tr.Gt.x; q.Ty[r] = tr.Gt.y;
-                    q.sp[r] = (uint32_t)tr.sp;
-                    const uint32_t st = q_status_of(tr);
-                    q.status[r] = st;
-                    finished = st == Q_FIN;
                 }
             }
             if (kind == Q_FIN) cF -= nsel;
@@ -883,6 +904,7 @@ struct EventPool {  // hands out the scene's events in order; they live until lj
 struct Tuning {
     int prim_min_lanes = kPrimMinLanes, refill = kRefillThreshold, track_refill = 24, shadow_chunk = 128, trav_min = 4, chunk = 64;
     int trace_kernel = 1, q_refill = 48, q_chunk = 128;
+    int q_blocks = 0, q_carveout = -1;  // resident CTAs of k_trace_q per SM (0: what fits), shared-memory carve-out in % (-1: the maximum)
     bool host_prof = false;
 };
 static const Tuning &tuning() {
@@ -900,6 +922,8 @@ static const Tuning &tuning() {
         geti("LJ_TRACE_KERNEL", v.trace_kernel, 0, 1);
         geti("LJ_Q_REFILL", v.q_refill, 1, kQRays);
         geti("LJ_Q_CHUNK", v.q_chunk, kQRays, 1 << 16);
+        geti("LJ_Q_BLOCKS", v.q_blocks, 0, 32);
+        geti("LJ_Q_CARVEOUT", v.q_carveout, -1, 100);
         v.host_prof = getenv("LJ_PROFILE_HOST") != nullptr;
         return v;
     }();
@@ -916,8 +940,9 @@ static int ensure_launch_geometry(lj_scene *s) {
     int sms = 0, a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, q0 = 0, q1 = 0;
     LJ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
     // k_trace_q keeps its ray tables in shared memory: ask for the largest carve-out so 8 CTAs stay resident
-    cudaFuncSetAttribute(k_trace_q<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(k_trace_q<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    const int carve = tuning().q_carveout >= 0 ? tuning().q_carveout : (int)cudaSharedmemCarveoutMaxShared;
+    cudaFuncSetAttribute(k_trace_q<0>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    cudaFuncSetAttribute(k_trace_q<1>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
     LJ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a0, k_trace<0>, 128, 0));
     LJ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a1, k_trace<1>, 128, 0));
     LJ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a2, k_trace<2>, 128, 0));
@@ -930,7 +955,7 @@ static int ensure_launch_geometry(lj_scene *s) {
     g.walk_blocks = sms * std::max(1, a2);
     g.step_blocks = sms * std::max(1, a4);
     g.flight_blocks = sms * std::max(1, a3);
-    g.q_blocks = sms * std::max(1, std::min(q0, q1));
+    g.q_blocks = sms * std::max(1, tuning().q_blocks > 0 ? std::min(tuning().q_blocks, std::min(q0, q1)) : std::min(q0, q1));
 #endif
     return LJ_OK;
 }
