@@ -135,12 +135,14 @@ def run_reference(args):
     saved = os.dup(1)
     os.dup2(devnull, 1)  # the reference prints a progress line per tile
     try:
+        shares = []
         for i in range(args.warmup + args.steps):
             c0 = oracle_lib.ray_counters()
-            img, s = ref.render(spp=spp)
+            img, s, share = oracle_lib.timed_render(ref, spp, cores)
             c1 = oracle_lib.ray_counters()
             if i >= args.warmup:
                 secs.append((s, c1[0] - c0[0] + c1[1] - c0[1]))
+                shares.append(share)
     finally:
         os.dup2(saved, 1)
         os.close(devnull)
@@ -155,7 +157,9 @@ def run_reference(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(key, w, h, full_spp), "timed_sample_spp": spp},
         "mrays_per_s": mrays,
-        "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": cores, "kind": "reference", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": cores, "kind": "reference", "sample": sample,
+                         "shim_share": sum(shares) / max(len(shares), 1),
+                         "shim_share_note": "fraction of the CPU time (all threads) spent inside the Embree-API shim's rtcIntersect1 / rtcOccluded1; real Embree would shrink this part"},
         "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -350,12 +354,13 @@ def main():
                 saved = os.dup(1)
                 os.dup2(devnull, 1)
                 try:
-                    _, secs = ref.render(spp=cs)
+                    _, secs, shim_share = oracle_lib.timed_render(ref, cs, cores)
                 finally:
                     os.dup2(saved, 1)
                     os.close(devnull)
                 line["cpu_baseline"] = {"value": npix * cs / secs / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "reference",
-                                        "sample": f"{key} {w}x{h} at {cs} spp, unmodified lajolla sources + Embree-API shim (lajolla+shim)"}
+                                        "sample": f"{key} {w}x{h} at {cs} spp, unmodified lajolla sources + Embree-API shim (lajolla+shim)",
+                                        "shim_share": shim_share}
             except Exception as e:  # the oracle is optional at bench time
                 line["cpu_baseline"] = {"value": None, "unit": "Msamples/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
         print(json.dumps(line), flush=True)

@@ -103,6 +103,18 @@ struct SceneImpl {
 };
 
 std::atomic<unsigned long long> g_closest{0}, g_any{0};
+// time-stamp-counter ticks spent inside rtcIntersect1 / rtcOccluded1, all threads (flushed every 1024 calls per thread):
+// the shim's share of the CPU render time, reported next to every "x CPU" figure (bench.py cpu_baseline.shim_share)
+std::atomic<unsigned long long> g_ticks{0};
+static inline unsigned long long shim_rdtsc() {
+#if defined(__x86_64__) || defined(__i386__)
+    unsigned lo, hi;
+    __asm__ __volatile__("rdtsc" : "=a"(lo), "=d"(hi));
+    return ((unsigned long long)hi << 32) | lo;
+#else
+    return 0;
+#endif
+}
 
 inline void release(GeomImpl *g) {
     if (g->refs.fetch_sub(1) == 1) delete g;
@@ -505,15 +517,19 @@ RTC_API void rtcSetGeometryIntersectFunction(RTCGeometry geometry, RTCIntersectF
 RTC_API void rtcSetGeometryOccludedFunction(RTCGeometry geometry, RTCOccludedFunctionN f) { ((GeomImpl *)geometry)->occluded_fn = f; }
 
 RTC_API void rtcIntersect1(RTCScene scene, struct RTCRayHit *rayhit, struct RTCIntersectArguments *) {
-    static thread_local unsigned long long local = 0;
-    if ((++local & 1023) == 0) g_closest.fetch_add(1024, std::memory_order_relaxed);
+    static thread_local unsigned long long local = 0, ticks = 0;
+    const unsigned long long t0 = shim_rdtsc();
     traverse<false>((SceneImpl *)scene, rayhit, nullptr);
+    ticks += shim_rdtsc() - t0;
+    if ((++local & 1023) == 0) { g_closest.fetch_add(1024, std::memory_order_relaxed); g_ticks.fetch_add(ticks, std::memory_order_relaxed); ticks = 0; }
 }
 
 RTC_API void rtcOccluded1(RTCScene scene, struct RTCRay *ray, struct RTCOccludedArguments *) {
-    static thread_local unsigned long long local = 0;
-    if ((++local & 1023) == 0) g_any.fetch_add(1024, std::memory_order_relaxed);
+    static thread_local unsigned long long local = 0, ticks = 0;
+    const unsigned long long t0 = shim_rdtsc();
     traverse<true>((SceneImpl *)scene, nullptr, ray);
+    ticks += shim_rdtsc() - t0;
+    if ((++local & 1023) == 0) { g_any.fetch_add(1024, std::memory_order_relaxed); g_ticks.fetch_add(ticks, std::memory_order_relaxed); ticks = 0; }
 }
 
 RTC_NAMESPACE_END
@@ -526,4 +542,10 @@ extern "C" void ljshim_get_counters(unsigned long long *closest, unsigned long l
 extern "C" void ljshim_reset_counters(void) {
     g_closest.store(0);
     g_any.store(0);
+    g_ticks.store(0);
+}
+// ticks inside the two ray-cast entry points (summed over threads) and the current time-stamp counter
+extern "C" void ljshim_get_ticks(unsigned long long *inside, unsigned long long *now) {
+    *inside = g_ticks.load();
+    *now = shim_rdtsc();
 }

@@ -52,6 +52,7 @@ def lib():
         l.ljo_render.argtypes = [C.c_void_p, C.c_void_p]
         l.ljo_film_size.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         l.ljshim_get_counters.argtypes = [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
+        l.ljshim_get_ticks.argtypes = [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
         atexit.register(l.ljo_shutdown)
         _lib = l
     return _lib
@@ -183,6 +184,23 @@ def ray_counters():
     a, b = C.c_ulonglong(0), C.c_ulonglong(0)
     lib().ljshim_get_counters(C.byref(a), C.byref(b))
     return a.value, b.value
+
+
+def shim_ticks():
+    """(time-stamp ticks spent inside rtcIntersect1 / rtcOccluded1 summed over threads, the counter now)."""
+    a, b = C.c_ulonglong(0), C.c_ulonglong(0)
+    lib().ljshim_get_ticks(C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+def timed_render(ref, spp, threads):
+    """ref.render(spp) plus the share of the CPU time that went into the Embree-API shim's ray casts:
+    ticks inside the shim (all threads) / (wall ticks * threads)."""
+    i0, n0 = shim_ticks()
+    img, secs = ref.render(spp=spp)
+    i1, n1 = shim_ticks()
+    share = (i1 - i0) / max((n1 - n0) * max(threads, 1), 1)
+    return img, secs, min(share, 1.0)
 
 
 # scene name -> xml path relative to SCENES
