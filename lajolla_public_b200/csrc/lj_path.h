@@ -35,6 +35,8 @@ struct PathPool {
                 // (volpath reuses sh_d.w as pdf_dir = pdf_scatter * G, < 0: no walk; sh_c.w as pdf_nee)
     // one bit per slot, one word per warp of the shade kernel: the slot carries an NEE shadow ray / walk this wave
     uint32_t *sh_mask;
+    // path integrator, scenes with Disney materials: the slots the first shade pass left for the second one (wavefront.cu)
+    uint32_t *class_queue;
     int capacity;
 };
 

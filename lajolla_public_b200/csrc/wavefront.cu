@@ -670,30 +670,66 @@ __global__ void __launch_bounds__(kQWarps * LJ_WARP_WIDTH, 8) k_trace_q(const LJ
 }
 
 
-// K4.  CLASS = kMatSmall: the kernel every path-integrator scene runs; in a scene WITH Disney materials it skips the
-// paths whose vertex carries one, and a second pass (CLASS = kMatDisney) shades those: one kernel per material class
-// ("material-sorted" at kernel granularity -- the slots stay where they are, each pass touches the records of its own
-// class only).  The first pass writes the sh_mask words, the second ORs its bits in.
+// K4.  CLASS = kMatSmall: the kernel every path-integrator scene runs.  In a scene WITH Disney materials
+// (split_classes) it shades the paths whose vertex carries one of the three small materials (or missed) and APPENDS
+// the slots of the others to pool.class_queue (one cursor atomic per block); the second pass (CLASS = kMatDisney)
+// runs one thread per QUEUE ENTRY, so its warps are full whatever fraction of the pool hit a Disney surface -- the
+// material-sorted shading of north_star at class granularity.  (Before the queue the second pass ran one thread per
+// slot: 9 of 32 lanes held a Disney vertex on disney_bsdf, profiles/r02l_disney_*.)  The records stay where they are;
+// the second pass gathers them through the queue.  The first pass writes the sh_mask words, the second ORs its bits in.
+constexpr int kCursorClass = 3;  // WaveArgs::cursors[3]: entries in pool.class_queue (path integrator only)
 template <int MIN_BLOCKS, int CLASS>
 __global__ void __launch_bounds__(128, MIN_BLOCKS) k_shade(const LJ_GRID_CONSTANT DevScene sc, const LJ_GRID_CONSTANT WaveArgs a, int split_classes) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
     ShadeCounters cnt = {0, 0, 0, 0};
-    bool has_shadow = false;
-    if (i < a.pool.capacity) {
-        uint32_t flags = f2u(a.pool.meta[i].y);
-        if ((flags & kAlive) && (!split_classes || path_material_class(sc, (int)f2u(a.pool.hit[i].w)) == CLASS)) {
+    if (CLASS == kMatDisney) {
+        if ((unsigned)t < a.cursors[kCursorClass]) {
+            const int i = (int)a.pool.class_queue[t];
             PathState s;
             load_state(a.pool, i, s);
             shade_path<CLASS>(sc, a.rp, s, cnt);
             store_state(a.pool, i, s, (s.flags & kAlive) != 0);
-            has_shadow = s.sh_tfar >= 0;
+            if (s.sh_tfar >= 0) atomicOr(&a.pool.sh_mask[i / LJ_WARP_WIDTH], 1u << (i % LJ_WARP_WIDTH));
         }
-    }
-    {   // capacity is a multiple of 256 (render_impl): whole warps are in range
-        unsigned m = __ballot_sync(0xffffffffu, has_shadow);
-        if (LJ_LANE() == 0 && i < a.pool.capacity) {
-            if (CLASS == kMatDisney) { if (m) a.pool.sh_mask[i / LJ_WARP_WIDTH] |= m; }
-            else a.pool.sh_mask[i / LJ_WARP_WIDTH] = m;
+    } else {
+        const int i = t;
+        bool has_shadow = false, queued = false;
+        if (i < a.pool.capacity) {
+            uint32_t flags = f2u(a.pool.meta[i].y);
+            if (flags & kAlive) {
+                if (!split_classes || path_material_class(sc, (int)f2u(a.pool.hit[i].w)) == CLASS) {
+                    PathState s;
+                    load_state(a.pool, i, s);
+                    shade_path<CLASS>(sc, a.rp, s, cnt);
+                    store_state(a.pool, i, s, (s.flags & kAlive) != 0);
+                    has_shadow = s.sh_tfar >= 0;
+                } else {
+                    queued = true;
+                }
+            }
+        }
+        {   // capacity is a multiple of 256 (render_impl): whole warps are in range
+            unsigned m = __ballot_sync(0xffffffffu, has_shadow);
+            if (LJ_LANE() == 0 && i < a.pool.capacity) a.pool.sh_mask[i / LJ_WARP_WIDTH] = m;
+        }
+        if (split_classes) {
+            const unsigned qm = __ballot_sync(0xffffffffu, queued);
+#if defined(LJ_HOSTSIM)
+            const unsigned base = queued ? atomicAdd(&a.cursors[kCursorClass], 1u) : 0u;
+#else
+            __shared__ unsigned s_q[4], s_qbase;
+            const int warp = threadIdx.x >> 5;
+            if (LJ_LANE() == 0) s_q[warp] = (unsigned)__popc(qm);
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                unsigned tot = 0;
+                for (int k = 0; k < 4; k++) { unsigned c = s_q[k]; s_q[k] = tot; tot += c; }
+                s_qbase = tot ? atomicAdd(&a.cursors[kCursorClass], tot) : 0u;
+            }
+            __syncthreads();
+            const unsigned base = s_qbase + s_q[warp];
+#endif
+            if (queued) a.pool.class_queue[base + (unsigned)__popc(qm & ((1u << LJ_LANE()) - 1u))] = (uint32_t)i;
         }
     }
     warp_add(&a.counters[C_BOUNCES_STRIPED + ((blockIdx.x * 4 + (threadIdx.x >> 5)) & (kStripes - 1))], cnt.bounces);
@@ -870,7 +906,9 @@ static int ensure_pool(lj_scene *s, int capacity, bool vol) {
     if (s->pool_capacity == capacity && s->pool_block && (s->pool.vol0 != nullptr) == vol) return LJ_OK;
     if (s->pool_block) { pool_block_give(s->device, s->pool_block, s->pool_bytes); s->pool_block = nullptr; }
     const int kFields = vol ? 14 : 9;
-    s->pool_block = pool_block_take(s->device, (size_t)capacity * sizeof(V4) * kFields + ((size_t)capacity + LJ_WARP_WIDTH - 1) / LJ_WARP_WIDTH * sizeof(uint32_t), &s->pool_bytes);
+    const size_t mask_words = ((size_t)capacity + LJ_WARP_WIDTH - 1) / LJ_WARP_WIDTH;
+    const size_t queue_words = (!vol && s->has_disney) ? (size_t)capacity : 0;  // class_queue of the Disney shade pass
+    s->pool_block = pool_block_take(s->device, (size_t)capacity * sizeof(V4) * kFields + (mask_words + queue_words) * sizeof(uint32_t), &s->pool_bytes);
     if (!s->pool_block) { s->pool_capacity = 0; return cuda_fail(cudaErrorMemoryAllocation, "path pool allocation"); }
     V4 *base = (V4 *)s->pool_block;
     PathPool &p = s->pool;
@@ -883,6 +921,7 @@ static int ensure_pool(lj_scene *s, int capacity, bool vol) {
         p.sh_o = base + (size_t)capacity * 12; p.sh_pl = base + (size_t)capacity * 13;
     }
     p.sh_mask = (uint32_t *)(base + (size_t)capacity * kFields);
+    p.class_queue = queue_words ? p.sh_mask + mask_words : nullptr;
     p.capacity = capacity;
     s->pool_capacity = capacity;
     return LJ_OK;

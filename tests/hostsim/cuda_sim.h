@@ -73,6 +73,7 @@ inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b)
 
 // device intrinsics, warp width 1
 template <typename T> inline T atomicAdd(T *p, T v) { T o = *p; *p = o + v; return o; }
+inline unsigned atomicOr(unsigned *p, unsigned v) { unsigned o = *p; *p = o | v; return o; }
 inline int atomicMin(int *p, int v) { int o = *p; *p = std::min(o, v); return o; }
 inline int atomicMax(int *p, int v) { int o = *p; *p = std::max(o, v); return o; }
 inline unsigned __ballot_sync(unsigned, bool p) { return p ? 1u : 0u; }
