@@ -109,41 +109,127 @@ LJ_HD V3 tracking_exp(V3 majorant_minus_min, float t) {
 
 LJ_HD int tracking_channel(float u) { return clampi((int)(u * 3), 0, 2); }
 
-// The two tracking loops, cut into single collision steps so the persistent kernels (wavefront.cu k_flight,
-// k_trace<2>) can run ONE step per lane per warp iteration and refill lanes whose segment ended, instead of
-// letting 31 lanes wait for the longest loop (measured on hetvol: 4 of 32 lanes active otherwise).
+// ---- local majorants ------------------------------------------------------------------------------------------
+// The reference bounds a heterogeneous medium by ONE number, the maximum of the density grid (medium.cpp:27-29), so a
+// ray through hetvol's box takes ~100 null collisions per segment although most of the box is empty.  The tracking
+// loops below bound it piecewise instead: DevVolume::maj holds the maximum of the grid over blocks of maj_block^3
+// voxel cells, a segment is tracked block by block with the block's own majorant, and a block that holds nothing is
+// crossed in one step.  Delta / ratio tracking are exact for ANY bound of the density (memorylessness of the
+// exponential: a tentative collision beyond the block face is discarded and redrawn in the next block), so the
+// estimators of homework2.tex:713-810 keep their expectation -- what changes is the random sequence, not the image
+// (tests: same mean as the global-majorant run, LJ_MAJ_BLOCK=0, and as the oracle's).  The three running products
+// stay consistent because both loops evaluate the same majorant function of the position.
+LJ_HD bool medium_has_local_majorant(const DevMedium &m) { return m.type != 0 && m.density.is_grid && m.density.maj != nullptr; }
+
+// Majorant (before the common scale) of the block that holds the point o + d t, and the parameter t_exit > t at which
+// the ray leaves it; outside the grid box: 0 and the parameter at which the ray enters the box (infinity if never).
+LJ_HD V3 volume_block_majorant(const DevVolume &v, V3 o, V3 d, float t, float &t_exit) {
+    const float hi[3] = {(float)(v.res[0] - 1), (float)(v.res[1] - 1), (float)(v.res[2] - 1)};
+    const V3 p = o + d * t;
+    const float pp[3] = {p.x, p.y, p.z}, dd[3] = {d.x, d.y, d.z};
+    float q[3], dq[3], fastest = 0;
+    bool inside = true;
+    for (int i = 0; i < 3; i++) {  // voxel coordinates, as volume_lookup
+        const float s = hi[i] / (v.p_max[i] - v.p_min[i]);
+        q[i] = (pp[i] - v.p_min[i]) * s;
+        dq[i] = dd[i] * s;
+        fastest = fmaxf(fastest, fabsf(dq[i]));
+        inside = inside && q[i] >= 0 && q[i] <= hi[i];
+    }
+    if (!(fastest > 0)) { t_exit = LJ_INF; return mk3(0); }
+    const float nudge = 1e-3f / fastest;  // lands a thousandth of a voxel beyond the face (the blocks are dilated by a node)
+    if (!inside) {
+        float t0 = 0, t1 = LJ_INF;
+        for (int i = 0; i < 3; i++) {
+            if (dq[i] != 0) {
+                float tn = (0 - q[i]) / dq[i], tf = (hi[i] - q[i]) / dq[i];
+                if (tn > tf) { float sw = tn; tn = tf; tf = sw; }
+                t0 = fmaxf(t0, tn); t1 = fminf(t1, tf);
+            } else if (q[i] < 0 || q[i] > hi[i]) {
+                t1 = -1;
+            }
+        }
+        t_exit = t0 <= t1 ? t + t0 + nudge : LJ_INF;
+        return mk3(0);
+    }
+    const float B = (float)v.maj_block;
+    int cell[3];
+    float te = LJ_INF;
+    for (int i = 0; i < 3; i++) {
+        cell[i] = clampi((int)(q[i] / B), 0, v.maj_res[i] - 1);
+        const float lo_face = (float)cell[i] * B, hi_face = fminf((float)(cell[i] + 1) * B, hi[i]);
+        if (dq[i] > 0) te = fminf(te, (hi_face - q[i]) / dq[i]);
+        else if (dq[i] < 0) te = fminf(te, (lo_face - q[i]) / dq[i]);
+    }
+    t_exit = t + fmaxf(te, 0.f) + nudge;
+    // One bound for the three channels (the largest): with per-channel block majorants a channel whose density is low
+    // in this block is sampled with few tentative collisions while the other channels' weights keep their full range,
+    // and the chromatic estimator's variance grows (measured on hetvol_colored: x1.5 .. x8, profiles/r02n_*); with a
+    // common bound every weight (majorant - sigma_t) / majorant stays in [0, 1].
+    return mk3(max3(xyz(ld4(&v.maj[(cell[2] * v.maj_res[1] + cell[1]) * v.maj_res[0] + cell[0]])))) * v.scale;
+}
+
+// sigma_t = sigma_a + sigma_s at p.  Heterogeneous: density * albedo + density * (1 - albedo) is the density itself
+// (heterogeneous.inl:3-21); the tracking loops only need this sum, so they skip the albedo grid's eight voxels.
+LJ_HD V3 medium_sigma_t(const DevMedium &m, V3 p) {
+    if (m.type == 0) return mk3(m.sigma_a[0] + m.sigma_s[0], m.sigma_a[1] + m.sigma_s[1], m.sigma_a[2] + m.sigma_s[2]);
+    return volume_lookup(m.density, p);
+}
+LJ_HD V3 safe_ratio(V3 a, V3 b) { return mk3(b.x > 0 ? a.x / b.x : 0.f, b.y > 0 ? a.y / b.y : 0.f, b.z > 0 ? a.z / b.z : 0.f); }
+
+// The two tracking loops, cut into single steps so the persistent kernels (wavefront.cu k_flight, k_trace<2|3>) can
+// run ONE step per lane per warp iteration and refill lanes whose segment ended, instead of letting 31 lanes wait
+// for the longest loop (measured on hetvol: 4 of 32 lanes active otherwise).  A step is one tentative collision in
+// the current majorant block, or the move into the next block.
 struct TrackState {
     V3 majorant, maj_rel;  // maj_rel = majorant - min(majorant), see tracking_exp
     float maj_c, max_maj;  // majorant of the sampled channel, max over channels
     float accum_t;
+    float t_block;         // the majorant holds up to this ray parameter (infinity: to the end of the segment)
     int channel, it;
 };
-// Draws the channel.  Returns false when the sampled channel has no majorant (nothing to track).
+LJ_HD void track_set_majorant(TrackState &ts, V3 majorant) {
+    ts.majorant = majorant;
+    ts.max_maj = max3(majorant);
+    ts.maj_c = comp(majorant, ts.channel);
+    ts.maj_rel = majorant - mk3(min3(majorant));
+}
+// Draws the channel.  Returns false when there is nothing to track (global majorant: the sampled channel has none).
 LJ_HD bool track_begin(const DevMedium &m, V3 o, V3 d, float ray_tfar, Pcg &rng, TrackState &ts) {
-    ts.majorant = medium_majorant(m, o, d, ray_tfar);
+    const bool local = medium_has_local_majorant(m);
+    const V3 global = local ? mk3(0) : medium_majorant(m, o, d, ray_tfar);
     ts.channel = tracking_channel(pcg_uniform(rng));
-    ts.max_maj = max3(ts.majorant);
-    ts.maj_c = comp(ts.majorant, ts.channel);
-    ts.maj_rel = ts.majorant - mk3(min3(ts.majorant));
     ts.accum_t = 0;
     ts.it = 0;
+    if (local) {
+        track_set_majorant(ts, volume_block_majorant(m.density, o, d, 0.f, ts.t_block));
+        return true;
+    }
+    track_set_majorant(ts, global);
+    ts.t_block = LJ_INF;
     return ts.maj_c > 0;
+}
+// the segment goes on beyond the current block: step into the next one (counted against the iteration limit, so a
+// ray that cannot advance still ends)
+LJ_HD void track_next_block(const DevMedium &m, V3 o, V3 d, TrackState &ts) {
+    track_set_majorant(ts, volume_block_majorant(m.density, o, d, ts.accum_t, ts.t_block));
+    ts.it++;
 }
 
 enum { kTrackContinue = 0, kTrackScatter = 1, kTrackEnd = 2 };
 
-// homework2.tex:713-758: one collision of the chromatic delta tracking free flight over [0, t_hit].
+// homework2.tex:713-758: one step of the chromatic delta tracking free flight over [0, t_hit].
 LJ_HD int flight_step(const DevMedium &m, V3 o, V3 d, float t_hit, int max_null, Pcg &rng, TrackState &ts,
                       V3 &transmittance, V3 &trans_dir_pdf, V3 &trans_nee_pdf) {
     if (ts.it >= max_null) return kTrackEnd;
-    float t = -logf(1 - pcg_uniform(rng)) / ts.maj_c;
-    float dt = t_hit - ts.accum_t;
-    ts.accum_t = fminf(ts.accum_t + t, t_hit);
+    const float t_end = fminf(ts.t_block, t_hit);
+    float t = LJ_INF;
+    if (ts.maj_c > 0) t = -logf(1 - pcg_uniform(rng)) / ts.maj_c;
+    float dt = t_end - ts.accum_t;
+    ts.accum_t = fminf(ts.accum_t + t, t_end);
     if (t < dt) {
-        V3 sa, ss;
-        medium_sigmas(m, o + d * ts.accum_t, sa, ss);
-        V3 sigma_t = sa + ss;
-        V3 real_prob = sigma_t / ts.majorant;
+        V3 sigma_t = medium_sigma_t(m, o + d * ts.accum_t);
+        V3 real_prob = safe_ratio(sigma_t, ts.majorant);
         V3 e = tracking_exp(ts.maj_rel, t);
         if (pcg_uniform(rng) < comp(real_prob, ts.channel)) {
             transmittance *= e / ts.max_maj;
@@ -160,21 +246,23 @@ LJ_HD int flight_step(const DevMedium &m, V3 o, V3 d, float t_hit, int max_null,
     transmittance *= e;
     trans_dir_pdf *= e;
     trans_nee_pdf *= e;
-    return kTrackEnd;
+    if (ts.t_block >= t_hit) return kTrackEnd;
+    track_next_block(m, o, d, ts);
+    return kTrackContinue;
 }
 
-// homework2.tex:771-810: one collision of ratio tracking over the shadow segment [0, next_t].
+// homework2.tex:771-810: one step of ratio tracking over the shadow segment [0, next_t].
 LJ_HD int ratio_step(const DevMedium &m, V3 o, V3 d, float next_t, int max_null, Pcg &rng, TrackState &ts,
                      V3 &T_light, V3 &p_trans_nee, V3 &p_trans_dir) {
     if (ts.it >= max_null) return kTrackEnd;
-    float t = -logf(1 - pcg_uniform(rng)) / ts.maj_c;
-    float dt = next_t - ts.accum_t;
-    ts.accum_t = fminf(ts.accum_t + t, next_t);
+    const float t_end = fminf(ts.t_block, next_t);
+    float t = LJ_INF;
+    if (ts.maj_c > 0) t = -logf(1 - pcg_uniform(rng)) / ts.maj_c;
+    float dt = t_end - ts.accum_t;
+    ts.accum_t = fminf(ts.accum_t + t, t_end);
     if (t < dt) {
-        V3 sa, ss;
-        medium_sigmas(m, o + d * ts.accum_t, sa, ss);
-        V3 sigma_t = sa + ss;
-        V3 real_prob = sigma_t / ts.majorant;
+        V3 sigma_t = medium_sigma_t(m, o + d * ts.accum_t);
+        V3 real_prob = safe_ratio(sigma_t, ts.majorant);
         V3 e = tracking_exp(ts.maj_rel, t);
         T_light *= e * (ts.majorant - sigma_t) / ts.max_maj;
         p_trans_nee *= e * ts.majorant / ts.max_maj;
@@ -187,7 +275,9 @@ LJ_HD int ratio_step(const DevMedium &m, V3 o, V3 d, float next_t, int max_null,
     T_light *= e;
     p_trans_nee *= e;
     p_trans_dir *= e;
-    return kTrackEnd;
+    if (ts.t_block >= next_t) return kTrackEnd;
+    track_next_block(m, o, d, ts);
+    return kTrackContinue;
 }
 
 // Whole loops (query seam, host simulation, and anything that is not a persistent kernel).

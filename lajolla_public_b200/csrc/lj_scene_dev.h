@@ -95,6 +95,11 @@ struct DevVolume {
     float scale;
     float max_data[3];  // volume.h get_max_value before scale
     const V4 *data;     // rgb0 per voxel, (z*ny+y)*nx+x
+    // Majorant grid of a density volume (null: none): the maximum of `data` over blocks of maj_block^3 voxel cells
+    // (one node of dilation), rgb0 per block, (z*my+y)*mx+x -- local majorants for the tracking loops (lj_media.h)
+    const V4 *maj;
+    int maj_res[3];
+    int maj_block;
 };
 struct DevMedium {
     int type;  // 0 homogeneous, 1 heterogeneous

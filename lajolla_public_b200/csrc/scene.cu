@@ -80,7 +80,14 @@ DevTexture conv_texture(const lj_texture_desc &t) {
 
 double lum(const float *c) { return c[0] * 0.212671 + c[1] * 0.715160 + c[2] * 0.072169; }
 
-DevVolume conv_volume(const lj_volume_desc &v, Uploader &up) {
+// Block size of the majorant grid of heterogeneous media in voxel cells (LJ_MAJ_BLOCK; 0: no grid, the tracking loops
+// use the reference's one global majorant, medium.cpp:27-29).
+int majorant_block() {  // (read at every lj_scene_create: the parity tests build one scene of each kind)
+    const char *e = getenv("LJ_MAJ_BLOCK");
+    return e ? std::min(64, std::max(0, atoi(e))) : 8;
+}
+
+DevVolume conv_volume(const lj_volume_desc &v, Uploader &up, bool want_majorant = false) {
     DevVolume d;
     memset(&d, 0, sizeof(d));
     d.is_grid = v.is_grid;
@@ -99,6 +106,33 @@ DevVolume conv_volume(const lj_volume_desc &v, Uploader &up) {
         }
         for (int c = 0; c < 3; c++) d.max_data[c] = mx[c];
         d.data = up.upload(tex);
+        const int B = majorant_block();
+        if (want_majorant && B > 0) {
+            // block (bx, by, bz) covers the voxel cells [b*B, (b+1)*B) per axis, i.e. the nodes b*B .. (b+1)*B of the
+            // trilinear lookup; one more node on either side keeps the bound valid for a point that sits a rounding
+            // error across the block face, and the factor covers the rounding of the interpolation weights
+            int mr[3];
+            for (int c = 0; c < 3; c++) mr[c] = std::max(1, (std::max(v.res[c] - 1, 1) + B - 1) / B);
+            std::vector<V4> maj((size_t)mr[0] * mr[1] * mr[2]);
+            for (int bz = 0; bz < mr[2]; bz++)
+                for (int by = 0; by < mr[1]; by++)
+                    for (int bx = 0; bx < mr[0]; bx++) {
+                        float m3[3] = {0, 0, 0};
+                        const int x0 = std::max(bx * B - 1, 0), x1 = std::min((bx + 1) * B + 1, v.res[0] - 1);
+                        const int y0 = std::max(by * B - 1, 0), y1 = std::min((by + 1) * B + 1, v.res[1] - 1);
+                        const int z0 = std::max(bz * B - 1, 0), z1 = std::min((bz + 1) * B + 1, v.res[2] - 1);
+                        for (int z = z0; z <= z1; z++)
+                            for (int y = y0; y <= y1; y++)
+                                for (int x = x0; x <= x1; x++) {
+                                    const float *px = v.data + 3 * (((size_t)z * v.res[1] + y) * v.res[0] + x);
+                                    for (int c = 0; c < 3; c++) m3[c] = std::max(m3[c], px[c]);
+                                }
+                        maj[((size_t)bz * mr[1] + by) * mr[0] + bx] = mk4(m3[0] * 1.000002f, m3[1] * 1.000002f, m3[2] * 1.000002f, 0.f);
+                    }
+            d.maj = up.upload(maj);
+            for (int c = 0; c < 3; c++) d.maj_res[c] = mr[c];
+            d.maj_block = B;
+        }
     }
     return d;
 }
@@ -681,7 +715,7 @@ static int scene_create_here(const lj_scene_desc *desc, lj_scene **out) {
         if (md.type == LJ_MEDIUM_HETEROGENEOUS) {
             s->has_grid_media = true;
             m.albedo = conv_volume(md.albedo, up);
-            m.density = conv_volume(md.density, up);
+            m.density = conv_volume(md.density, up, true);
         }
     }
     for (int i = 0; i < desc->num_materials; i++) if (desc->materials[i].type >= LJ_MAT_DISNEY_DIFFUSE) s->has_disney = true;

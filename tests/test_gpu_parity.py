@@ -234,6 +234,45 @@ def test_image_parity_homework_configs(oracle, name, spp):
     assert s["block_z_rms"] <= 1.15 * null["block_z_rms"] + 0.02, (s, null)
 
 
+@pytest.mark.parametrize("name,spp", [("hetvol", 32), ("hetvol_colored", 32)])
+def test_local_majorants_keep_the_expectation(oracle, name, spp):
+    """The tracking loops bound a grid medium block by block (lj_media.h) where the reference uses one global majorant
+    (medium.cpp:27-29).  Same estimator, different random sequence: (i) the NEE walks (ratio tracking + MIS weight)
+    have the same mean contribution with and without the majorant grid, (ii) so do the images (mean within 1 %, tile z
+    statistics no worse than two renders of the same kind give each other)."""
+    old = os.environ.get("LJ_MAJ_BLOCK")
+    try:
+        os.environ["LJ_MAJ_BLOCK"] = "0"
+        sc_global = lj.parse_scene(oracle.scene_ljs(name))
+    finally:
+        if old is None:
+            os.environ.pop("LJ_MAJ_BLOCK", None)
+        else:
+            os.environ["LJ_MAJ_BLOCK"] = old
+    sc, ref = pair(oracle, name)
+    q = pc.make_walk_queries(sc, ref, 1 << 18)
+    q["medium_id"] = np.where(q["medium_id"] < 0, 0, q["medium_id"])  # every walk starts inside a medium
+    a, b = sc.nee_walks(q).astype(np.float64), sc_global.nee_walks(q).astype(np.float64)
+    assert np.all(np.isfinite(a)) and np.all(np.isfinite(b))
+    se = np.sqrt(a.var(axis=0) / len(a) + b.var(axis=0) / len(b))
+    zw = (a.mean(axis=0) - b.mean(axis=0)) / np.maximum(se, 1e-30)
+    img, var = sc.render(spp=spp, variance=True)
+    st = sc.last_stats
+    img_g, var_g = sc_global.render(spp=spp, variance=True)
+    st_g = sc_global.last_stats
+    img_g2, _ = sc_global.render(spp=spp, variance=True, seed=0x5eed5eed5eed)
+    null = pc.image_stats(img_g2, img_g, var_g, var_g)
+    s = pc.image_stats(img, img_g, var, var_g)
+    record("local_majorants", dict(scene=name, spp=spp, walk_mean=a.mean(axis=0).tolist(), walk_mean_global=b.mean(axis=0).tolist(), walk_z=zw.tolist(),
+                                   ms=st.render_ms, ms_global=st_g.render_ms, **s, null={k: null[k] for k in ("frac_z_gt_3", "block_frac_z_gt_4", "block_z_rms")}))
+    sc_global.close()
+    assert np.abs(zw).max() < 4.5, (zw, a.mean(axis=0), b.mean(axis=0))
+    assert np.allclose(img.mean(axis=(0, 1)), img_g.mean(axis=(0, 1)), rtol=0.01), s
+    assert s["frac_z_gt_3"] <= 1.25 * null["frac_z_gt_3"] + 0.003, (s, null)
+    assert s["block_frac_z_gt_4"] <= 1.25 * null["block_frac_z_gt_4"] + 0.003, (s, null)
+    assert s["block_z_rms"] <= 1.15 * null["block_z_rms"] + 0.02, (s, null)
+
+
 @pytest.mark.parametrize("name", ["cbox", "veach_mi", "matpreview", "disney_bsdf", "volpath_test6", "hetvol"])
 def test_golden_vectors(oracle, name):
     """The CUDA kernels against the committed fixtures (tests/golden, answers of the reference's object code)."""
