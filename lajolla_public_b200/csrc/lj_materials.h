@@ -617,4 +617,17 @@ LJ_HD_CALL bool bsdf_sample_call(const DevScene &sc, const MatCtx &c, V3 wi, con
     return bsdf_sample<kMatDisney>(sc, c, wi, vx, u, w, s);
 }
 
+// The same for every material (the volpath integrator's shade kernel: surfaces are the rare event there, and the five
+// inlined all-material dispatchers made k_shade_vol 1.6 MB of SASS -- 7 of every 8 stall cycles waiting for instructions)
+LJ_HD_CALL MatCtx mat_ctx_all_call(const DevScene &sc, const DevMaterial &m, const Vertex &vx) { return mat_ctx<kMatAll>(sc, m, vx); }
+LJ_HD_CALL V3 bsdf_eval_all_call(const DevScene &sc, const MatCtx &c, V3 wi, V3 wo, const Vertex &vx, int transport) {
+    return bsdf_eval<kMatAll>(sc, c, wi, wo, vx, transport);
+}
+LJ_HD_CALL float bsdf_pdf_all_call(const DevScene &sc, const MatCtx &c, V3 wi, V3 wo, const Vertex &vx) {
+    return bsdf_pdf<kMatAll>(sc, c, wi, wo, vx);
+}
+LJ_HD_CALL bool bsdf_sample_all_call(const DevScene &sc, const MatCtx &c, V3 wi, const Vertex &vx, V2 u, float w, BsdfSample &s) {
+    return bsdf_sample<kMatAll>(sc, c, wi, vx, u, w, s);
+}
+
 }  // namespace lj

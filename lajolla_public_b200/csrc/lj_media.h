@@ -195,8 +195,10 @@ LJ_HD void track_set_majorant(TrackState &ts, V3 majorant) {
     ts.maj_rel = majorant - mk3(min3(majorant));
 }
 // Draws the channel.  Returns false when there is nothing to track (global majorant: the sampled channel has none).
+// GRID = false: the caller knows the scene has no grid medium (the block logic is compiled out).
+template <bool GRID = true>
 LJ_HD bool track_begin(const DevMedium &m, V3 o, V3 d, float ray_tfar, Pcg &rng, TrackState &ts) {
-    const bool local = medium_has_local_majorant(m);
+    const bool local = GRID && medium_has_local_majorant(m);
     const V3 global = local ? mk3(0) : medium_majorant(m, o, d, ray_tfar);
     ts.channel = tracking_channel(pcg_uniform(rng));
     ts.accum_t = 0;
@@ -219,10 +221,11 @@ LJ_HD void track_next_block(const DevMedium &m, V3 o, V3 d, TrackState &ts) {
 enum { kTrackContinue = 0, kTrackScatter = 1, kTrackEnd = 2 };
 
 // homework2.tex:713-758: one step of the chromatic delta tracking free flight over [0, t_hit].
+template <bool GRID = true>
 LJ_HD int flight_step(const DevMedium &m, V3 o, V3 d, float t_hit, int max_null, Pcg &rng, TrackState &ts,
                       V3 &transmittance, V3 &trans_dir_pdf, V3 &trans_nee_pdf) {
     if (ts.it >= max_null) return kTrackEnd;
-    const float t_end = fminf(ts.t_block, t_hit);
+    const float t_end = GRID ? fminf(ts.t_block, t_hit) : t_hit;
     float t = LJ_INF;
     if (ts.maj_c > 0) t = -logf(1 - pcg_uniform(rng)) / ts.maj_c;
     float dt = t_end - ts.accum_t;
@@ -246,7 +249,7 @@ LJ_HD int flight_step(const DevMedium &m, V3 o, V3 d, float t_hit, int max_null,
     transmittance *= e;
     trans_dir_pdf *= e;
     trans_nee_pdf *= e;
-    if (ts.t_block >= t_hit) return kTrackEnd;
+    if (!GRID || ts.t_block >= t_hit) return kTrackEnd;
     track_next_block(m, o, d, ts);
     return kTrackContinue;
 }

@@ -100,7 +100,11 @@ LJ_HD void shade_vol_path(const DevScene &sc, const RenderParams &rp, PathState 
         V3 sa;
         medium_sigmas(sc.media[s.medium], p, sa, sigma_s);
     }
-    const DevMaterial *mat = scatter ? nullptr : &sc.materials[vx.material_id];
+    // (one material context per vertex -- the principled BSDF's parameter textures are read once -- and out-of-line
+    //  dispatchers: lj_materials.h)
+    MatCtx mc;
+    mc.m = nullptr;
+    if (!scatter) mc = mat_ctx_all_call(sc, sc.materials[vx.material_id], vx);
     {
         float lu = pcg_uniform(rng), lv = pcg_uniform(rng);
         float light_w = pcg_uniform(rng), shape_w = pcg_uniform(rng);
@@ -120,8 +124,8 @@ LJ_HD void shade_vol_path(const DevScene &sc, const RenderParams &rp, PathState 
                     f = sigma_s * phase_eval(m, dir_view, dir_light);
                     pdf_scatter = phase_pdf(m, dir_view, dir_light);
                 } else {
-                    f = bsdf_eval(sc, *mat, dir_view, dir_light, vx, 0);
-                    pdf_scatter = bsdf_pdf(sc, *mat, dir_view, dir_light, vx);
+                    f = bsdf_eval_all_call(sc, mc, dir_view, dir_light, vx, 0);
+                    pdf_scatter = bsdf_pdf_all_call(sc, mc, dir_view, dir_light, vx);
                 }
                 V3 Le = light_emission(sc, light, -dir_light, 0.f, pl);
                 V3 c = s.T * f * Le * (G / pdf_nee);
@@ -158,11 +162,11 @@ LJ_HD void shade_vol_path(const DevScene &sc, const RenderParams &rp, PathState 
     } else {
         float bu = pcg_uniform(rng), bv = pcg_uniform(rng), bw = pcg_uniform(rng);
         BsdfSample bs;
-        if (!bsdf_sample(sc, *mat, dir_view, vx, mk2(bu, bv), bw, bs)) { cnt.finished++; s.rng_state = rng.state; return; }
+        if (!bsdf_sample_all_call(sc, mc, dir_view, vx, mk2(bu, bv), bw, bs)) { cnt.finished++; s.rng_state = rng.state; return; }
         next_dir = bs.dir_out;
         if (bs.eta != 0) s.eta_scale /= (bs.eta * bs.eta);
-        V3 f = bsdf_eval(sc, *mat, dir_view, next_dir, vx, 0);
-        float pdf = bsdf_pdf(sc, *mat, dir_view, next_dir, vx);
+        V3 f = bsdf_eval_all_call(sc, mc, dir_view, next_dir, vx, 0);
+        float pdf = bsdf_pdf_all_call(sc, mc, dir_view, next_dir, vx);
         if (!(pdf > 0)) { cnt.finished++; s.rng_state = rng.state; return; }
         s.T = s.T * f / pdf;
         s.pdf_sa = pdf;

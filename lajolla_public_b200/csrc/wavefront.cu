@@ -56,6 +56,7 @@ struct WaveArgs {
     // image-space split (lj_render_opts.split == LJ_SPLIT_TILES): this call renders the 8x4 pixel tiles t with
     // t % tile_stride == tile_offset; a sample split leaves tile_stride = 1
     int tile_stride, tile_offset, tiles_local;
+    int walk_whole_groups;  // k_trace<2|3>: test a lane's whole primitive group in one pass (trees of a few nodes)
 };
 
 __device__ __forceinline__ void warp_add(unsigned long long *ctr, unsigned v) {
@@ -323,6 +324,14 @@ __global__ void __launch_bounds__(128, MODE >= 2 ? LJ_WALK_MIN_BLOCKS : (MODE ==
                     if (has_p) {
                         prim_tests++;
                         if (trav_prim<SHADOW>(sc.prims, tr)) trav_terminate(tr);  // any-hit ends at the first hit
+                        if (WALK && a.walk_whole_groups) {
+                            // walk kernels, scenes whose primitives sit in a handful of groups (hetvol: 15 primitives under
+                            // the root): the whole group in this pass.  A pass is shared with lanes that wait to track,
+                            // and one pass per primitive kept the warp at 6 lanes (hetvol 154 -> 166 Msamples/s); with a
+                            // real hierarchy the groups are short and waiting for the longest one costs more than it saves
+                            // (vol_cbox_teapot: walk stage +18 %), so render_impl sets this for tiny trees only.
+                            while (tr.Gt.y != 0) { prim_tests++; trav_prim<SHADOW>(sc.prims, tr); }
+                        }
                     }
                 } else if ((lane == 0 ? (void)node_passes++ : (void)0), work) {
                     bool descend = !has_p;
@@ -740,6 +749,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_shade(const LJ_GRID_CONSTAN
 // surface reached, or null-collision limit) write the result and are refilled from the cursor once fewer than
 // track_refill lanes are busy.  Result per path: thr *= transmittance / avg(trans_dir_pdf) (:814-816), the MIS caches
 // vol0 / vol1 *= the two pdf products (:521-558), rng state, and hit = (distance, kScatter) on a real collision.
+template <bool GRID>
 __global__ void __launch_bounds__(128) k_flight(const LJ_GRID_CONSTANT DevScene sc, const LJ_GRID_CONSTANT WaveArgs a) {
     const unsigned n = (unsigned)a.pool.capacity;
     unsigned int *cursor = &a.cursors[2];
@@ -785,7 +795,7 @@ __global__ void __launch_bounds__(128) k_flight(const LJ_GRID_CONSTANT DevScene 
                         rng.state = (uint64_t)f2u(m.z) | ((uint64_t)f2u(m.w) << 32);
                         rng.inc = pcg_inc(path_stream((uint64_t)f2u(m.x) * a.rp.spp_total + f2u(x.z)));
                         tr = mk3(1); pd = mk3(1); pn = mk3(1);
-                        if (track_begin(sc.media[medium], o, d, rd.w, rng, ts)) busy = true;
+                        if (track_begin<GRID>(sc.media[medium], o, d, rd.w, rng, ts)) busy = true;
                         else a.pool.meta[idx] = mk4(m.x, m.y, u2f((uint32_t)rng.state), u2f((uint32_t)(rng.state >> 32)));  // channel draw only
                     }
                 }
@@ -800,7 +810,7 @@ __global__ void __launch_bounds__(128) k_flight(const LJ_GRID_CONSTANT DevScene 
             if (bm == 0) break;
             if (!first && !drained && __popc(bm) < a.track_refill) break;
             if (busy) {
-                int r = flight_step(sc.media[medium], o, d, t_hit, sc.options.max_null_collisions, rng, ts, tr, pd, pn);
+                int r = flight_step<GRID>(sc.media[medium], o, d, t_hit, sc.options.max_null_collisions, rng, ts, tr, pd, pn);
                 if (r != kTrackContinue) {
                     V4 t = a.pool.thr[slot], v0 = a.pool.vol0[slot], v1 = a.pool.vol1[slot], m = a.pool.meta[slot];
                     float inv = 1 / avg3(pd);
@@ -986,7 +996,12 @@ static int ensure_launch_geometry(lj_scene *s) {
     LJ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a1, k_trace<1>, 128, 0));
     LJ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a2, k_trace<2>, 128, 0));
     LJ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a4, k_trace<3>, 128, 0));
-    LJ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a3, k_flight, 128, 0));
+    LJ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a3, k_flight<true>, 128, 0));
+    {   // (the variant for scenes without grid media never needs more registers)
+        int a3h = 0;
+        LJ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a3h, k_flight<false>, 128, 0));
+        a3 = std::min(a3, a3h);
+    }
     LJ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q0, k_trace_q<0>, kQWarps * LJ_WARP_WIDTH, 0));
     LJ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q1, k_trace_q<1>, kQWarps * LJ_WARP_WIDTH, 0));
     sms = std::max(1, sms);
@@ -1021,6 +1036,7 @@ static void fill_trace_args(lj_scene *s, WaveArgs &a) {
     a.q_refill = std::min(t.q_refill, kQRays);  // (the host simulation has 2 ray slots per "warp")
     a.q_chunk = t.q_chunk;
     a.one_bits = 0x3f800000u;
+    a.walk_whole_groups = s->info.num_bvh_nodes <= 4 ? 1 : 0;
     a.qstack = (U2 *)s->d_qstack;
     a.qdepth = s->qdepth;
     a.cursors = s->d_cursors;
@@ -1161,7 +1177,11 @@ static int render_impl(lj_scene *s, const lj_render_opts *opts_in, float *d_out,
         else launch_trace(s, a, 0, stream);
         LJ_CUDA(cudaEventRecord(e2, stream));
         if (vol) {
-            if (sc.num_media > 0) { LJ_LAUNCH(k_flight, g.flight_blocks, 128, stream, sc, a); launches++; }
+            if (sc.num_media > 0) {
+                if (s->has_grid_media) LJ_LAUNCH(k_flight<true>, g.flight_blocks, 128, stream, sc, a);
+                else LJ_LAUNCH(k_flight<false>, g.flight_blocks, 128, stream, sc, a);
+                launches++;
+            }
             LJ_LAUNCH(k_shade_vol, nb128, 128, stream, sc, a);
         } else {
             // one pass per material class; the classes are disjoint and a path's class is read from its hit record,
