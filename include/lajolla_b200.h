@@ -235,7 +235,7 @@ int lj_trace_any(lj_scene *scene, const lj_ray *rays, int64_t n, uint8_t *occlud
  *   LJ_TRACE_WAVEFRONT_LANE   same, through the one-ray-per-lane persistent kernels (the volpath integrator's)
  * For the wavefront any-hit kernels rays[].tnear must equal the scene's shadow epsilon (lj_scene_info). */
 enum { LJ_TRACE_PLAIN = 0, LJ_TRACE_WAVEFRONT = 1, LJ_TRACE_WAVEFRONT_LANE = 2,
-       LJ_TRACE_WALK_WHOLE = 3, LJ_TRACE_WALK_STEP = 4 /* lj_nee_walk_batch: the persistent walk kernels, below */ };
+       LJ_TRACE_WALK_WHOLE = 3, LJ_TRACE_WALK_STEP = 4, LJ_TRACE_WALK_STAGED = 5 /* lj_nee_walk_batch: the walk kernels, below */ };
 typedef struct lj_trace_opts {
     int32_t kernel;      /* LJ_TRACE_* */
     int32_t pool_paths;  /* path-pool slots (0: sized to the batch); batches larger than the pool run in rounds */
@@ -248,7 +248,7 @@ int lj_trace_any_ex(lj_scene *scene, const lj_ray *rays, int64_t n, const lj_tra
 /* The volpath integrator's next-event-estimation WALK (homework2.tex:459-510 + 771-810): from `origin` towards
  * `light_point` through index-matched surfaces, ratio tracking over every segment inside a medium, blocked by the
  * first surface with a material or by the bounce budget.  contribution_rgb[3*i..] = c * T * MIS weight / pdf of walk i
- * (0 if blocked).  opts->kernel: LJ_TRACE_PLAIN (one thread per walk, whole loops), LJ_TRACE_WALK_WHOLE / _STEP (the
+ * (0 if blocked).  opts->kernel: LJ_TRACE_PLAIN (one thread per walk, whole loops), LJ_TRACE_WALK_WHOLE / _STEP / _STAGED (the
  * persistent kernels lj_render launches for homogeneous / grid media: walks loaded into the path pool).  The random
  * numbers of walk i come from a stream that depends on (i, seed) only, so all three give bit-identical answers. */
 typedef struct lj_walk_query {

@@ -93,7 +93,7 @@ class lj_trace_opts(C.Structure):
     _fields_ = [("kernel", i32), ("pool_paths", i32), ("slot_stride", i32), ("_pad", i32)]
 
 
-LJ_TRACE_PLAIN, LJ_TRACE_WAVEFRONT, LJ_TRACE_WAVEFRONT_LANE, LJ_TRACE_WALK_WHOLE, LJ_TRACE_WALK_STEP = 0, 1, 2, 3, 4
+LJ_TRACE_PLAIN, LJ_TRACE_WAVEFRONT, LJ_TRACE_WAVEFRONT_LANE, LJ_TRACE_WALK_WHOLE, LJ_TRACE_WALK_STEP, LJ_TRACE_WALK_STAGED = 0, 1, 2, 3, 4, 5
 
 
 class lj_walk_query(C.Structure):

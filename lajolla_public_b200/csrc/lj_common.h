@@ -66,6 +66,24 @@ LJ_HD float length_squared(V3 a) { return dot(a, a); }
 LJ_HD float length(V3 a) { return sqrtf(dot(a, a)); }
 LJ_HD float distance(V3 a, V3 b) { return length(a - b); }
 LJ_HD float distance_squared(V3 a, V3 b) { return length_squared(a - b); }
+// The same sums with the rounding of every step spelled out.  `x*x + y*y + z*z` may be contracted to FMAs in more
+// than one way, and the compiler's pick depends on the code around the expression: quantities that several KERNELS
+// must reproduce bit for bit (the length of a walk segment, wavefront.cu) are formed with these.
+LJ_HD float dot_fixed(V3 a, V3 b) {
+#if defined(__CUDA_ARCH__)
+    return __fmaf_rn(a.z, b.z, __fmaf_rn(a.y, b.y, __fmul_rn(a.x, b.x)));
+#else
+    return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x));
+#endif
+}
+LJ_HD float distance_fixed(V3 a, V3 b) { V3 v = a - b; return sqrtf(dot_fixed(v, v)); }
+LJ_HD float sum_squares_fixed(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fmaf_rn(b, b, __fmul_rn(a, a));
+#else
+    return fmaf(b, b, a * a);
+#endif
+}
 // vector.h:249-257: zero vector stays zero.
 LJ_HD V3 normalize(V3 a) {
     float l = length(a);

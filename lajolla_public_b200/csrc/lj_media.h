@@ -255,10 +255,11 @@ LJ_HD int flight_step(const DevMedium &m, V3 o, V3 d, float t_hit, int max_null,
 }
 
 // homework2.tex:771-810: one step of ratio tracking over the shadow segment [0, next_t].
+template <bool GRID = true>
 LJ_HD int ratio_step(const DevMedium &m, V3 o, V3 d, float next_t, int max_null, Pcg &rng, TrackState &ts,
                      V3 &T_light, V3 &p_trans_nee, V3 &p_trans_dir) {
     if (ts.it >= max_null) return kTrackEnd;
-    const float t_end = fminf(ts.t_block, next_t);
+    const float t_end = GRID ? fminf(ts.t_block, next_t) : next_t;
     float t = LJ_INF;
     if (ts.maj_c > 0) t = -logf(1 - pcg_uniform(rng)) / ts.maj_c;
     float dt = t_end - ts.accum_t;
@@ -278,7 +279,7 @@ LJ_HD int ratio_step(const DevMedium &m, V3 o, V3 d, float next_t, int max_null,
     T_light *= e;
     p_trans_nee *= e;
     p_trans_dir *= e;
-    if (ts.t_block >= next_t) return kTrackEnd;
+    if (!GRID || ts.t_block >= next_t) return kTrackEnd;
     track_next_block(m, o, d, ts);
     return kTrackContinue;
 }

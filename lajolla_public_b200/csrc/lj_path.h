@@ -33,6 +33,15 @@ struct PathPool {
     V4 *sh_o;   // walk origin.xyz, bits((medium + 1) & 0xffff | budget << 16)
     V4 *sh_pl;  // light point.xyz, bits(walk rng seed)
                 // (volpath reuses sh_d.w as pdf_dir = pdf_scatter * G, < 0: no walk; sh_c.w as pdf_nee)
+    // volpath, staged NEE walk (wavefront.cu k_walk_begin / k_walk_track): the walk's current segment in the layout the
+    // closest-hit kernel reads (ray_o / ray_d / hit / meta of a "walk view" of the pool) and its running products
+    V4 *w_o;    // segment origin.xyz, tnear
+    V4 *w_d;    // direction.xyz, tfar
+    V4 *w_hit;  // t, u, v, bits(prim) of the segment
+    V4 *w_meta; // -, bits(kAlive while the walk is in flight), bits(rng lo), bits(rng hi)
+    V4 *w_T;    // T_light.xyz, bits(index-matched surfaces crossed)
+    V4 *w_pn;   // p_trans_nee.xyz, bits(current medium)
+    V4 *w_pd;   // p_trans_dir.xyz, bits(budget)
     // one bit per slot, one word per warp of the shade kernel: the slot carries an NEE shadow ray / walk this wave
     uint32_t *sh_mask;
     // path integrator, scenes with Disney materials: the slots the first shade pass left for the second one (wavefront.cu)

@@ -213,7 +213,7 @@ LJ_HD Pcg walk_rng(uint64_t path_id, uint32_t walk_seed, uint64_t seed) {
 // tnear / tfar of the next segment
 LJ_HD void nee_walk_segment(const DevScene &sc, const NeeWalk &w, float &tnear, float &tfar) {
     tnear = sc.shadow_eps;
-    tfar = (1 - sc.shadow_eps) * distance(w.pc, w.pl);
+    tfar = (1 - sc.shadow_eps) * distance_fixed(w.pc, w.pl);
 }
 
 // Geometric normal of a hit flipped to the shading-normal side, as intersect() leaves it
@@ -241,7 +241,7 @@ LJ_HD void hit_medium_interface(const DevScene &sc, V3 org, V3 dir, const Hit &h
 }
 
 // Length of the segment just traversed (to the surface hit, or to the light point).
-LJ_HD float nee_walk_next_t(const NeeWalk &w, const Hit &hit) { return hit.prim != kNoHit ? hit.t : distance(w.pc, w.pl); }
+LJ_HD float nee_walk_next_t(const NeeWalk &w, const Hit &hit) { return hit.prim != kNoHit ? hit.t : distance_fixed(w.pc, w.pl); }
 
 // After ratio tracking over the segment: opaque / index-matched test.  Returns true when the walk is over;
 // `contribution` is then what the path's radiance gains (zero if blocked).
@@ -262,7 +262,8 @@ LJ_HD bool nee_walk_decide(const DevScene &sc, NeeWalk &w, const Hit &hit, V3 &c
     if (max3(w.T_light) > 0) {
         float pdf_nee = w.pdf_nee * avg3(w.p_nee);
         float pdf_dir = w.pdf_dir * avg3(w.p_dir);
-        if (pdf_nee > 0) contribution = w.c * w.T_light * (mis_power(pdf_nee, pdf_dir) / avg3(w.p_nee));
+        // (power heuristic with its sum of squares rounded in a fixed order, see dot_fixed)
+        if (pdf_nee > 0) contribution = w.c * w.T_light * ((pdf_nee * pdf_nee) / sum_squares_fixed(pdf_nee, pdf_dir) / avg3(w.p_nee));
     }
     return true;
 }

@@ -10,7 +10,7 @@
 #include "lj_path.h"
 
 namespace lj {
-struct LaunchGeom { int trace_blocks = 0, walk_blocks = 1, step_blocks = 1, flight_blocks = 1, q_blocks = 1; };
+struct LaunchGeom { int trace_blocks = 0, walk_blocks = 1, step_blocks = 1, flight_blocks = 1, q_blocks = 1, wtrack_blocks = 1; };
 }  // namespace lj
 
 struct lj_scene {

@@ -57,6 +57,7 @@ struct WaveArgs {
     // t % tile_stride == tile_offset; a sample split leaves tile_stride = 1
     int tile_stride, tile_offset, tiles_local;
     int walk_whole_groups;  // k_trace<2|3>: test a lane's whole primitive group in one pass (trees of a few nodes)
+    int closest_counter;    // k_trace_q<0>: the counter its rays are added to (C_CLOSEST; C_SHADOW for walk segments)
 };
 
 __device__ __forceinline__ void warp_add(unsigned long long *ctr, unsigned v) {
@@ -671,7 +672,7 @@ __global__ void __launch_bounds__(kQWarps * LJ_WARP_WIDTH, 8) k_trace_q(const LJ
             __syncwarp();
         }
     }
-    warp_add(&a.counters[MODE == 0 ? C_CLOSEST : C_SHADOW], traced);
+    warp_add(&a.counters[MODE == 0 ? a.closest_counter : C_SHADOW], traced);
     warp_add(&a.counters[C_NODE_STEPS], node_steps);
     warp_add(&a.counters[C_PRIM_TESTS], prim_tests);
     warp_add(&a.counters[C_NODE_PASSES], lane == 0 ? node_passes : 0u);  // (warp-uniform counters)
@@ -826,24 +827,229 @@ __global__ void __launch_bounds__(128) k_flight(const LJ_GRID_CONSTANT DevScene 
     }
 }
 
+// ---- K3 for grid media, staged.  k_trace<3> runs a whole NEE walk in one lane -- traversal of a segment, ratio
+// tracking over it, the index-matched test, the next segment -- and its passes alternate between traversal steps and
+// tracking steps with the lanes in the other state idle (10 of 32 lanes per instruction on hetvol_colored, 77 % of the
+// stall cycles waiting for instructions: profiles/r02o_*).  Here the walk state lives in the pool between stages and
+// each stage is a lean kernel:  k_walk_begin (first segment of every walk the shade kernel left) -> rounds of
+// [k_trace_q<0> over the "walk view" of the pool (closest hit of every pending segment: the kernel the path integrator
+// extends with) -> k_walk_track (ratio tracking over the segment, one step per lane per pass as k_flight, then the
+// opaque / index-matched test: contribution added, or the next segment written)] -> k_walk_finish (the few walks that
+// cross more surfaces than there were rounds, whole loops).  Same step functions and the same PCG draws in the same
+// order as the serial walk: results are bit-identical (test_walk_kernels_parity).
+constexpr int kWalkRounds = 3;
+
+__global__ void __launch_bounds__(256) k_walk_begin(const LJ_GRID_CONSTANT DevScene sc, const LJ_GRID_CONSTANT WaveArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.pool.capacity) return;
+    V4 wm = mk4(0, 0, 0, 0);
+    if ((a.pool.sh_mask[i / LJ_WARP_WIDTH] >> (i % LJ_WARP_WIDTH)) & 1u) {
+        const V4 sd = a.pool.sh_d[i], so = a.pool.sh_o[i], pl = a.pool.sh_pl[i];
+        const uint32_t mb = f2u(so.w);
+        NeeWalk wk;
+        wk.pc = xyz(so); wk.dir = xyz(sd); wk.pl = xyz(pl);
+        const uint64_t path_id = (uint64_t)f2u(a.pool.meta[i].x) * a.rp.spp_total + f2u(a.pool.aux[i].z);
+        const Pcg rng = walk_rng(path_id, f2u(pl.w), a.rp.seed);
+        float tn, tf;
+        nee_walk_segment(sc, wk, tn, tf);
+        a.pool.w_o[i] = mk4(wk.pc, tn);
+        a.pool.w_d[i] = mk4(wk.dir, tf);
+        a.pool.w_T[i] = mk4(1, 1, 1, u2f(0u));
+        a.pool.w_pn[i] = mk4(1, 1, 1, u2f((uint32_t)((int)(mb & 0xffffu) - 1)));
+        a.pool.w_pd[i] = mk4(1, 1, 1, u2f(mb >> 16));
+        wm = mk4(0, u2f(kAlive), u2f((uint32_t)rng.state), u2f((uint32_t)(rng.state >> 32)));
+    }
+    a.pool.w_meta[i] = wm;
+}
+
+// the walk of slot i as the stages left it (c, the two pdfs and the light point stay in the shade kernel's records)
+LJ_HD void walk_load(const PathPool &p, const RenderParams &rp, int i, const V4 &wm, NeeWalk &wk, float &seg_tnear, float &seg_tfar) {
+    const V4 o = p.w_o[i], d = p.w_d[i], T = p.w_T[i], pn = p.w_pn[i], pd = p.w_pd[i], pl = p.sh_pl[i];
+    wk.pc = xyz(o); wk.dir = xyz(d); wk.pl = xyz(pl);
+    seg_tnear = o.w; seg_tfar = d.w;
+    wk.T_light = xyz(T); wk.p_nee = xyz(pn); wk.p_dir = xyz(pd);
+    wk.shadow_bounces = f2u(T.w); wk.medium = (int)f2u(pn.w); wk.budget = f2u(pd.w);
+    const uint64_t path_id = (uint64_t)f2u(p.meta[i].x) * rp.spp_total + f2u(p.aux[i].z);
+    wk.rng.state = (uint64_t)f2u(wm.z) | ((uint64_t)f2u(wm.w) << 32);
+    wk.rng.inc = pcg_inc(path_stream(path_id) + (((uint64_t)f2u(pl.w) << 1) | 1ull));  // as walk_rng
+}
+// the segment is tracked: opaque / index-matched test, then the contribution or the next segment
+LJ_HD void walk_decide_store(const DevScene &sc, const PathPool &p, int i, NeeWalk &wk, const Hit &hit) {
+    const V4 cc = p.sh_c[i];
+    wk.c = xyz(cc); wk.pdf_nee = cc.w; wk.pdf_dir = p.sh_d[i].w;
+    V3 contrib;
+    if (nee_walk_decide(sc, wk, hit, contrib)) {
+        if (max3(contrib) > 0 || min3(contrib) < 0 || contrib.x != contrib.x || contrib.y != contrib.y || contrib.z != contrib.z) {
+            V4 r = p.rad[i];
+            p.rad[i] = mk4(r.x + contrib.x, r.y + contrib.y, r.z + contrib.z, r.w);
+        }
+        p.w_meta[i] = mk4(0, 0, 0, 0);
+        return;
+    }
+    float tn, tf;
+    nee_walk_segment(sc, wk, tn, tf);
+    p.w_o[i] = mk4(wk.pc, tn);
+    p.w_d[i] = mk4(wk.dir, tf);
+    p.w_T[i] = mk4(wk.T_light, u2f(wk.shadow_bounces));
+    p.w_pn[i] = mk4(wk.p_nee, u2f((uint32_t)wk.medium));
+    p.w_pd[i] = mk4(wk.p_dir, u2f(wk.budget));
+    p.w_meta[i] = mk4(0, u2f(kAlive), u2f((uint32_t)wk.rng.state), u2f((uint32_t)(wk.rng.state >> 32)));
+}
+
+__global__ void __launch_bounds__(128) k_walk_track(const LJ_GRID_CONSTANT DevScene sc, const LJ_GRID_CONSTANT WaveArgs a) {
+    const unsigned n = (unsigned)a.pool.capacity;
+    unsigned int *cursor = &a.cursors[1];
+    const int lane = LJ_LANE();
+    const unsigned chunk = (unsigned)a.chunk;
+    unsigned chunk_next = 0, chunk_end = 0;
+    bool drained = false, global_out = false;
+    bool busy = false, tracking = false;
+    int slot = -1;
+    NeeWalk wk;
+    wk.medium = -1; wk.pc = mk3(0); wk.dir = mk3(0); wk.T_light = mk3(1); wk.p_nee = mk3(1); wk.p_dir = mk3(1);
+    wk.rng.state = 0; wk.rng.inc = 1;
+    Hit hit;
+    hit.prim = kNoHit; hit.t = 0; hit.u = 0; hit.v = 0;
+    float next_t = 0;
+    TrackState ts;
+    for (;;) {
+        unsigned want = drained ? 0u : __ballot_sync(0xffffffffu, !busy);
+        if (want) {
+            const unsigned cnt = (unsigned)__popc(want);
+            const unsigned lim = chunk_end < n ? chunk_end : n;
+            const unsigned left = chunk_next < lim ? lim - chunk_next : 0u;
+            unsigned nb = 0;
+            bool fresh = false;
+            if (cnt > left && !global_out) {
+                if (lane == 0) nb = atomicAdd(cursor, chunk);
+                nb = __shfl_sync(0xffffffffu, nb, 0);
+                if (nb >= n) global_out = true; else fresh = true;
+            }
+            const unsigned rank = (unsigned)__popc(want & ((1u << lane) - 1));
+            const unsigned idx = rank < left ? chunk_next + rank : (fresh ? nb + (rank - left) : 0xffffffffu);
+            if (fresh) { chunk_next = nb + (cnt - left); chunk_end = nb + chunk; }
+            else chunk_next += cnt < left ? cnt : left;
+            drained = global_out && chunk_next >= (chunk_end < n ? chunk_end : n);
+            if (!busy && idx < n) {
+                const V4 wm = a.pool.w_meta[idx];
+                if (f2u(wm.y) & kAlive) {
+                    slot = (int)idx;
+                    float tn, seg_tfar;
+                    walk_load(a.pool, a.rp, slot, wm, wk, tn, seg_tfar);
+                    const V4 h = a.pool.w_hit[slot];
+                    hit.t = h.x; hit.u = h.y; hit.v = h.z; hit.prim = (int)f2u(h.w);
+                    next_t = nee_walk_next_t(wk, hit);
+                    tracking = wk.medium >= 0 && track_begin(sc.media[wk.medium], wk.pc, wk.dir, seg_tfar, wk.rng, ts);
+                    busy = true;
+                }
+            }
+        }
+        if (!__ballot_sync(0xffffffffu, busy)) {
+            if (drained) break;
+            continue;
+        }
+        for (bool first = true;; first = false) {
+            const unsigned bm = __ballot_sync(0xffffffffu, busy);
+            if (bm == 0) break;
+            if (!first && !drained && __popc(bm) < a.track_refill) break;
+            if (busy) {
+                if (tracking && ratio_step(sc.media[wk.medium], wk.pc, wk.dir, next_t, sc.options.max_null_collisions, wk.rng, ts,
+                                                 wk.T_light, wk.p_nee, wk.p_dir) != kTrackContinue) tracking = false;
+                if (!tracking) {
+                    walk_decide_store(sc, a.pool, slot, wk, hit);
+                    busy = false;
+                }
+            }
+        }
+    }
+}
+
+// the walks still in flight after the last round (more index-matched surfaces than rounds): whole loops, one thread each
+__global__ void __launch_bounds__(128) k_walk_finish(const LJ_GRID_CONSTANT DevScene sc, const LJ_GRID_CONSTANT WaveArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.pool.capacity) return;
+    const V4 wm = a.pool.w_meta[i];
+    if (!(f2u(wm.y) & kAlive)) return;
+    NeeWalk wk;
+    float tn, tf;
+    walk_load(a.pool, a.rp, i, wm, wk, tn, tf);
+    const V4 cc = a.pool.sh_c[i];
+    wk.c = xyz(cc); wk.pdf_nee = cc.w; wk.pdf_dir = a.pool.sh_d[i].w;
+    V3 contrib = mk3(0);
+    for (int guard = 0; guard < 1 << 16; guard++) {
+        Hit hit;
+        trace8<false>(sc.nodes8, sc.prims, wk.pc, wk.dir, tn, tf, hit);
+        const float next_t = nee_walk_next_t(wk, hit);
+        if (wk.medium >= 0) ratio_track(sc.media[wk.medium], wk.pc, wk.dir, tf, next_t, sc.options.max_null_collisions, wk.rng, wk.T_light, wk.p_nee, wk.p_dir);
+        if (nee_walk_decide(sc, wk, hit, contrib)) break;
+        nee_walk_segment(sc, wk, tn, tf);
+    }
+    if (max3(contrib) > 0 || min3(contrib) < 0 || contrib.x != contrib.x || contrib.y != contrib.y || contrib.z != contrib.z) {
+        V4 r = a.pool.rad[i];
+        a.pool.rad[i] = mk4(r.x + contrib.x, r.y + contrib.y, r.z + contrib.z, r.w);
+    }
+    a.pool.w_meta[i] = mk4(0, 0, 0, 0);
+}
+
 // K4 + K5 for the volpath integrator (lj_volpath.h)
+// PASS 0: one thread per slot; shades the medium events (scattering, index-matched boundaries, escapes) and appends the
+// slots whose vertex lies on a surface WITH a material to pool.class_queue; PASS 1: one thread per queue entry shades
+// those -- full warps in the BSDF code instead of a few lanes of every warp (the same queue as the Disney pass of the
+// path integrator; before it k_shade_vol ran at 13.6 lanes per instruction, profiles/r02o_*).
+LJ_HD bool vol_vertex_has_material(const DevScene &sc, int prim) {
+    return prim >= 0 && sc.shapes[prim_shape_id(ld4(&sc.prims[prim].c))].material_id >= 0;
+}
+template <int PASS>
 __global__ void __launch_bounds__(128) k_shade_vol(const LJ_GRID_CONSTANT DevScene sc, const LJ_GRID_CONSTANT WaveArgs a) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
     ShadeCounters cnt = {0, 0, 0, 0};
-    bool has_shadow = false;
-    if (i < a.pool.capacity) {
-        uint32_t flags = f2u(a.pool.meta[i].y);
-        if (flags & kAlive) {
+    if (PASS == 1) {
+        if ((unsigned)t < a.cursors[kCursorClass]) {
+            const int i = (int)a.pool.class_queue[t];
             PathState s;
             load_state_vol(a.pool, i, s);
             shade_vol_path(sc, a.rp, s, cnt);
             store_state_vol(a.pool, i, s, (s.flags & kAlive) != 0);
-            has_shadow = s.sh_pdf_dir >= 0;
+            if (s.sh_pdf_dir >= 0) atomicOr(&a.pool.sh_mask[i / LJ_WARP_WIDTH], 1u << (i % LJ_WARP_WIDTH));
         }
-    }
-    {
-        unsigned m = __ballot_sync(0xffffffffu, has_shadow);
-        if (LJ_LANE() == 0 && i < a.pool.capacity) a.pool.sh_mask[i / LJ_WARP_WIDTH] = m;
+    } else {
+        const int i = t;
+        bool has_shadow = false, queued = false;
+        if (i < a.pool.capacity) {
+            uint32_t flags = f2u(a.pool.meta[i].y);
+            if (flags & kAlive) {
+                if (vol_vertex_has_material(sc, (int)f2u(a.pool.hit[i].w))) {
+                    queued = true;
+                } else {
+                    PathState s;
+                    load_state_vol(a.pool, i, s);
+                    shade_vol_path(sc, a.rp, s, cnt);
+                    store_state_vol(a.pool, i, s, (s.flags & kAlive) != 0);
+                    has_shadow = s.sh_pdf_dir >= 0;
+                }
+            }
+        }
+        {
+            unsigned m = __ballot_sync(0xffffffffu, has_shadow);
+            if (LJ_LANE() == 0 && i < a.pool.capacity) a.pool.sh_mask[i / LJ_WARP_WIDTH] = m;
+        }
+        const unsigned qm = __ballot_sync(0xffffffffu, queued);
+#if defined(LJ_HOSTSIM)
+        const unsigned base = queued ? atomicAdd(&a.cursors[kCursorClass], 1u) : 0u;
+#else
+        __shared__ unsigned s_q[4], s_qbase;
+        const int warp = threadIdx.x >> 5;
+        if (LJ_LANE() == 0) s_q[warp] = (unsigned)__popc(qm);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned tot = 0;
+            for (int k = 0; k < 4; k++) { unsigned c = s_q[k]; s_q[k] = tot; tot += c; }
+            s_qbase = tot ? atomicAdd(&a.cursors[kCursorClass], tot) : 0u;
+        }
+        __syncthreads();
+        const unsigned base = s_qbase + s_q[warp];
+#endif
+        if (queued) a.pool.class_queue[base + (unsigned)__popc(qm & ((1u << LJ_LANE()) - 1u))] = (uint32_t)i;
     }
     warp_add(&a.counters[C_BOUNCES_STRIPED + ((blockIdx.x * 4 + (threadIdx.x >> 5)) & (kStripes - 1))], cnt.bounces);
 }
@@ -915,9 +1121,9 @@ __global__ void __launch_bounds__(128) k_aux(const LJ_GRID_CONSTANT DevScene sc,
 static int ensure_pool(lj_scene *s, int capacity, bool vol) {
     if (s->pool_capacity == capacity && s->pool_block && (s->pool.vol0 != nullptr) == vol) return LJ_OK;
     if (s->pool_block) { pool_block_give(s->device, s->pool_block, s->pool_bytes); s->pool_block = nullptr; }
-    const int kFields = vol ? 14 : 9;
+    const int kFields = vol ? 21 : 9;
     const size_t mask_words = ((size_t)capacity + LJ_WARP_WIDTH - 1) / LJ_WARP_WIDTH;
-    const size_t queue_words = (!vol && s->has_disney) ? (size_t)capacity : 0;  // class_queue of the Disney shade pass
+    const size_t queue_words = (vol || s->has_disney) ? (size_t)capacity : 0;  // class_queue of the second shade pass
     s->pool_block = pool_block_take(s->device, (size_t)capacity * sizeof(V4) * kFields + (mask_words + queue_words) * sizeof(uint32_t), &s->pool_bytes);
     if (!s->pool_block) { s->pool_capacity = 0; return cuda_fail(cudaErrorMemoryAllocation, "path pool allocation"); }
     V4 *base = (V4 *)s->pool_block;
@@ -926,7 +1132,11 @@ static int ensure_pool(lj_scene *s, int capacity, bool vol) {
     p.thr = base + (size_t)capacity * 3; p.rad = base + (size_t)capacity * 4; p.sh_d = base + (size_t)capacity * 5;
     p.sh_c = base + (size_t)capacity * 6; p.meta = base + (size_t)capacity * 7; p.aux = base + (size_t)capacity * 8;
     p.vol0 = p.vol1 = p.vol2 = p.sh_o = p.sh_pl = nullptr;
+    p.w_o = p.w_d = p.w_hit = p.w_meta = p.w_T = p.w_pn = p.w_pd = nullptr;
     if (vol) {
+        p.w_o = base + (size_t)capacity * 14; p.w_d = base + (size_t)capacity * 15; p.w_hit = base + (size_t)capacity * 16;
+        p.w_meta = base + (size_t)capacity * 17; p.w_T = base + (size_t)capacity * 18; p.w_pn = base + (size_t)capacity * 19;
+        p.w_pd = base + (size_t)capacity * 20;
         p.vol0 = base + (size_t)capacity * 9; p.vol1 = base + (size_t)capacity * 10; p.vol2 = base + (size_t)capacity * 11;
         p.sh_o = base + (size_t)capacity * 12; p.sh_pl = base + (size_t)capacity * 13;
     }
@@ -953,6 +1163,7 @@ struct EventPool {  // hands out the scene's events in order; they live until lj
 struct Tuning {
     int prim_min_lanes = kPrimMinLanes, refill = kRefillThreshold, track_refill = 24, shadow_chunk = 128, trav_min = 4, chunk = 64;
     int trace_kernel = 1, q_refill = 48, q_chunk = 128;
+    int walk_kernel = 1;  // volpath NEE walk: 0 = k_trace<2|3> (one lane per walk), 1 = staged kernels for grid media, 2 = staged for every scene
     int q_blocks = 0, q_carveout = -1;  // resident CTAs of k_trace_q per SM (0: what fits), shared-memory carve-out in % (-1: the maximum)
     bool host_prof = false;
 };
@@ -969,6 +1180,7 @@ static const Tuning &tuning() {
         geti("LJ_TRAV_MIN", v.trav_min, 1, 32);
         geti("LJ_CHUNK", v.chunk, 32, 1 << 16);
         geti("LJ_TRACE_KERNEL", v.trace_kernel, 0, 1);
+        geti("LJ_WALK_KERNEL", v.walk_kernel, 0, 2);
         geti("LJ_Q_REFILL", v.q_refill, 1, kQRays);
         geti("LJ_Q_CHUNK", v.q_chunk, kQRays, 1 << 16);
         geti("LJ_Q_BLOCKS", v.q_blocks, 0, 32);
@@ -984,7 +1196,7 @@ static int ensure_launch_geometry(lj_scene *s) {
     LaunchGeom &g = s->geom;
     if (g.trace_blocks > 0) return LJ_OK;
 #if defined(LJ_HOSTSIM)
-    g.trace_blocks = g.walk_blocks = g.step_blocks = g.flight_blocks = g.q_blocks = 1;
+    g.trace_blocks = g.walk_blocks = g.step_blocks = g.flight_blocks = g.q_blocks = g.wtrack_blocks = 1;
 #else
     int sms = 0, a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, q0 = 0, q1 = 0;
     LJ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
@@ -1009,6 +1221,11 @@ static int ensure_launch_geometry(lj_scene *s) {
     g.walk_blocks = sms * std::max(1, a2);
     g.step_blocks = sms * std::max(1, a4);
     g.flight_blocks = sms * std::max(1, a3);
+    {
+        int w0 = 0;
+        LJ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w0, k_walk_track, 128, 0));
+        g.wtrack_blocks = sms * std::max(1, w0);
+    }
     g.q_blocks = sms * std::max(1, tuning().q_blocks > 0 ? std::min(tuning().q_blocks, std::min(q0, q1)) : std::min(q0, q1));
 #endif
     return LJ_OK;
@@ -1037,6 +1254,7 @@ static void fill_trace_args(lj_scene *s, WaveArgs &a) {
     a.q_chunk = t.q_chunk;
     a.one_bits = 0x3f800000u;
     a.walk_whole_groups = s->info.num_bvh_nodes <= 4 ? 1 : 0;
+    a.closest_counter = C_CLOSEST;
     a.qstack = (U2 *)s->d_qstack;
     a.qdepth = s->qdepth;
     a.cursors = s->d_cursors;
@@ -1053,6 +1271,29 @@ static void launch_trace(lj_scene *s, const WaveArgs &a, int mode, cudaStream_t 
         if (mode == 0) LJ_LAUNCH(k_trace<0>, s->geom.trace_blocks, 128, stream, sc, a);
         else LJ_LAUNCH(k_trace<1>, s->geom.trace_blocks, 128, stream, sc, a);
     }
+}
+
+// NEE walk stage of one volpath wave in its staged form (k_walk_begin ... k_walk_finish above)
+// (default: scenes with grid media, and scenes with a real hierarchy -- there the queue-form traversal kernel beats the
+//  one-ray-per-lane loop of k_trace<2>: vol_cbox_teapot walk stage 265 -> 227 ms per 256 spp; on the few-primitive test
+//  scenes k_trace<2> with whole primitive groups is faster, volpath_test6 71 vs 115 ms)
+static bool walk_staged(const lj_scene *s) {
+    return tuning().walk_kernel == 2 || (tuning().walk_kernel == 1 && (s->has_grid_media || s->info.num_bvh_nodes > 64));
+}
+static uint64_t launch_walk_staged(lj_scene *s, const WaveArgs &a, cudaStream_t stream) {
+    const DevScene &sc = s->dev;
+    const int nb256 = (a.pool.capacity + 255) / 256, nb128 = (a.pool.capacity + 127) / 128;
+    LJ_LAUNCH(k_walk_begin, nb256, 256, stream, sc, a);
+    WaveArgs v = a;  // the walk view of the pool: the pending segments are the "rays", w_meta says which slots hold one
+    v.pool.ray_o = a.pool.w_o; v.pool.ray_d = a.pool.w_d; v.pool.hit = a.pool.w_hit; v.pool.meta = a.pool.w_meta;
+    v.closest_counter = C_SHADOW;
+    for (int r = 0; r < kWalkRounds; r++) {
+        cudaMemsetAsync(s->d_cursors, 0, 2 * sizeof(unsigned int), stream);
+        LJ_LAUNCH(k_trace_q<0>, s->geom.q_blocks, kQWarps * LJ_WARP_WIDTH, stream, sc, v);
+        LJ_LAUNCH(k_walk_track, s->geom.wtrack_blocks, 128, stream, sc, a);
+    }
+    LJ_LAUNCH(k_walk_finish, nb128, 128, stream, sc, a);
+    return 2 + 2 * kWalkRounds;
 }
 
 static int ensure_render_buffers(lj_scene *s, int npix, bool want_sq) {
@@ -1182,7 +1423,9 @@ static int render_impl(lj_scene *s, const lj_render_opts *opts_in, float *d_out,
                 else LJ_LAUNCH(k_flight<false>, g.flight_blocks, 128, stream, sc, a);
                 launches++;
             }
-            LJ_LAUNCH(k_shade_vol, nb128, 128, stream, sc, a);
+            LJ_LAUNCH(k_shade_vol<0>, nb128, 128, stream, sc, a);
+            LJ_LAUNCH(k_shade_vol<1>, nb128, 128, stream, sc, a);
+            launches++;
         } else {
             // one pass per material class; the classes are disjoint and a path's class is read from its hit record,
             // which the shade passes do not modify: every live path is shaded exactly once per wave
@@ -1190,7 +1433,8 @@ static int render_impl(lj_scene *s, const lj_render_opts *opts_in, float *d_out,
             if (s->has_disney) { LJ_LAUNCH((k_shade<4, kMatDisney>), nb128, 128, stream, sc, a, 1); launches++; }
         }
         LJ_CUDA(cudaEventRecord(e3, stream));
-        if (vol && s->has_grid_media) LJ_LAUNCH(k_trace<3>, g.step_blocks, 128, stream, sc, a);
+        if (vol && walk_staged(s)) launches += launch_walk_staged(s, a, stream) - 1;
+        else if (vol && s->has_grid_media) LJ_LAUNCH(k_trace<3>, g.step_blocks, 128, stream, sc, a);
         else if (vol) LJ_LAUNCH(k_trace<2>, g.walk_blocks, 128, stream, sc, a);
         else launch_trace(s, a, 1, stream);
         LJ_CUDA(cudaEventRecord(e4, stream));
@@ -1462,7 +1706,8 @@ static int walk_batch_impl(lj_scene *s, const lj_walk_query *q, int64_t n, const
             cudaMemsetAsync(s->d_cursors, 0, 4 * sizeof(unsigned int), stream);
             cudaMemsetAsync(s->d_counters, 0, sizeof(unsigned long long) * C_TOTAL, stream);
             cudaEventRecord(s->ev[0], stream);
-            if (kernel == LJ_TRACE_WALK_STEP) LJ_LAUNCH(k_trace<3>, s->geom.step_blocks, 128, stream, s->dev, a);
+            if (kernel == LJ_TRACE_WALK_STAGED) launch_walk_staged(s, a, stream);
+            else if (kernel == LJ_TRACE_WALK_STEP) LJ_LAUNCH(k_trace<3>, s->geom.step_blocks, 128, stream, s->dev, a);
             else LJ_LAUNCH(k_trace<2>, s->geom.walk_blocks, 128, stream, s->dev, a);
             cudaEventRecord(s->ev[1], stream);
             LJ_LAUNCH(k_pool_store_walks, (m + 255) / 256, 256, stream, s->pool, m, stride, d_out + 3 * done);
@@ -1504,7 +1749,7 @@ extern "C" int lj_trace_any_ex(lj_scene *s, const lj_ray *rays, int64_t n, const
 
 extern "C" int lj_nee_walk_batch(lj_scene *s, const lj_walk_query *q, int64_t n, const lj_trace_opts *opts, float *contribution_rgb, double *kernel_ms) {
     if (!s || !q || !contribution_rgb || n < 0) { set_error("invalid argument"); return LJ_ERR_INVALID; }
-    if (opts && opts->kernel != LJ_TRACE_PLAIN && opts->kernel != LJ_TRACE_WALK_WHOLE && opts->kernel != LJ_TRACE_WALK_STEP) { set_error("unknown walk kernel"); return LJ_ERR_INVALID; }
+    if (opts && opts->kernel != LJ_TRACE_PLAIN && opts->kernel != LJ_TRACE_WALK_WHOLE && opts->kernel != LJ_TRACE_WALK_STEP && opts->kernel != LJ_TRACE_WALK_STAGED) { set_error("unknown walk kernel"); return LJ_ERR_INVALID; }
     if (n == 0) return LJ_OK;
     DeviceGuard guard(s->device);
     return walk_batch_impl(s, q, n, opts, contribution_rgb, kernel_ms);

@@ -20,8 +20,7 @@ def build():
 def sim_lib():
     global _sim
     if _sim is None:
-        if not os.path.exists(SIM_SO):
-            build()
+        build()  # (make is incremental: a stale library would silently test old code)
         lib = C.CDLL(SIM_SO)
         for name, (res, args) in abi.PROTOTYPES.items():
             fn = getattr(lib, name)

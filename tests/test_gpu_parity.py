@@ -54,7 +54,7 @@ def test_ray_parity(oracle, name):
     record("ray_parity", dict(scene=name, primary=r1, bounce=r2, occlusion_agree=occ))
 
 
-@pytest.mark.parametrize("name", ["cbox", "sponza", "disney_bsdf", "vol_cbox_teapot"])
+@pytest.mark.parametrize("name", ["cbox", "sponza", "disney_bsdf", "vol_cbox_teapot", "veach_mi"])
 def test_wavefront_kernels_ray_parity(oracle, name):
     """Parity test 1 on the kernels that actually render: k_trace_q<0|1> (queue form, the path integrator's) and
     k_trace<0|1> (lane form) fed through the path pool exactly as lj_render launches them, with pools that are full,
@@ -95,12 +95,13 @@ def test_pixel_filters(oracle, name):
 
 @pytest.mark.parametrize("name", ["volpath_test6", "vol_cbox_teapot", "hetvol", "hetvol_colored"])
 def test_walk_kernels_parity(oracle, name):
-    """The volpath NEE-walk kernels k_trace<2> (whole tracking loops) and k_trace<3> (one collision per pass, traversal
-    and tracking phases voted per warp) against the serial walk, bit for bit, with full, sparse and multi-round pools."""
+    """The volpath NEE-walk kernels k_trace<2> (whole tracking loops), k_trace<3> (one collision per pass, traversal
+    and tracking phases voted per warp) and the staged form (k_walk_begin -> [k_trace_q<0> over the walk view ->
+    k_walk_track] x rounds -> k_walk_finish) against the serial walk, bit for bit, with full, sparse and multi-round pools."""
     from lajolla_public_b200 import abi
     sc, ref = pair(oracle, name)
-    W, S = abi.LJ_TRACE_WALK_WHOLE, abi.LJ_TRACE_WALK_STEP
-    cfg = [(W, 0, 1), (W, 0, 7), (W, 20000, 1), (S, 0, 1), (S, 0, 37), (S, 30000, 3), (S, 1000, 1)]
+    W, S, G = abi.LJ_TRACE_WALK_WHOLE, abi.LJ_TRACE_WALK_STEP, abi.LJ_TRACE_WALK_STAGED
+    cfg = [(W, 0, 1), (W, 0, 7), (W, 20000, 1), (S, 0, 1), (S, 0, 37), (S, 30000, 3), (S, 1000, 1), (G, 0, 1), (G, 0, 37), (G, 30000, 3), (G, 1000, 1)]
     record("walk_parity", dict(scene=name, **pc.check_walk_parity(sc, ref, 1 << 16, cfg)))
 
 
