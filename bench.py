@@ -266,6 +266,7 @@ def main():
         agg["extend_launches"] += st.extend_launches; agg["samples"] += st.samples; agg["waves"] += st.waves
         agg["node_steps"] += st.node_steps; agg["prim_tests"] += st.prim_tests
         agg["node_passes"] += st.node_passes; agg["prim_passes"] += st.prim_passes
+        agg["pool_paths"] = int(st.pool_paths)
     e1.record(stream)
     barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
@@ -315,7 +316,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(key, w, h, full_spp), "spp_per_gpu": (s_end - s_begin) if tile_stride == 0 else total_spp, "image_spp": total_spp,
-                       "l2_policy": f"path pool (4M slots x {224 if key in VOLPATH else 144} B) streams through HBM every wave, larger than the 126 MB L2",
+                       "l2_policy": f"path pool ({agg.get('pool_paths', 0)} slots x {336 if key in VOLPATH else 144} B) streams through HBM every wave, larger than the 126 MB L2",
                        "scene_source": "reference scene flattened to .ljs", "parallelism": f"{args.split}-split x{world} + NCCL reduce (NCCL_NVLS_ENABLE={os.environ.get('NCCL_NVLS_ENABLE', 'default')})" if world > 1 else "single GPU"},
             "mrays_per_s": (agg["closest"] + agg["shadow"]) * world / (ms_total / 1e3) / 1e6,
             "rays_per_sample": (agg["closest"] + agg["shadow"]) / max(agg["samples"], 1),

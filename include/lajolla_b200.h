@@ -164,7 +164,7 @@ typedef struct lj_render_opts {
     int32_t sample_end;    /* both 0 => [0, spp).  PCG stream of a path = hash(pixel*spp + sample)    */
     int32_t normalize;     /* 1: divide by (sample_end-sample_begin) like render.cpp:94; 0: raw sums */
     int32_t pool_paths;    /* path slots resident in HBM (rounded up to a multiple of 256, at least 1024);
-                              0: sized to the work, at most 1<<22 */
+                              0: sized to the work, at most 1<<23 */
     uint64_t seed;         /* 0 => pcg.h:33 default seed */
     float *variance_out;   /* optional host w*h*3: per-pixel sample variance of the mean (NULL to skip) */
     /* Image-space share of this call (the reference's decomposition is image tiles, render.cpp:75-100): only the

@@ -323,6 +323,42 @@ void pool_block_give(int device, void *block, size_t bytes) {
     }
     if (old) cudaFree(old);  // (cudaFree works on a pointer of any device)
 }
+
+// The small per-scene render buffers that must stay plain cudaMalloc / cudaMallocHost memory (the films are read by peer
+// GPUs and by NCCL, the counters are pinned) are recycled the same way: on a shared node a cudaFree / cudaFreeHost
+// sometimes blocks for 0.1 - 1 s (measured: lj_scene_destroy 2 .. 950 ms, profiles/r02y_diag_e2e.txt), which a
+// scene-per-render caller paid on every call.  A handful of spares per process; exact size match.
+namespace {
+struct SpareBuffer { int kind, device; void *ptr; size_t bytes; };
+std::vector<SpareBuffer> g_spares;
+constexpr size_t kMaxSpares = 8;
+void spare_release(const SpareBuffer &b) { if (b.kind == kSpareHost) cudaFreeHost(b.ptr); else cudaFree(b.ptr); }
+}  // namespace
+void *spare_take(int kind, int device, size_t bytes) {
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mutex);
+        for (size_t i = 0; i < g_spares.size(); i++)
+            if (g_spares[i].kind == kind && g_spares[i].device == device && g_spares[i].bytes == bytes) {
+                void *p = g_spares[i].ptr;
+                g_spares.erase(g_spares.begin() + (long)i);
+                return p;
+            }
+    }
+    void *p = nullptr;
+    DeviceGuard guard(device);
+    cudaError_t e = kind == kSpareHost ? cudaMallocHost(&p, bytes) : cudaMalloc(&p, bytes);
+    return e == cudaSuccess ? p : nullptr;
+}
+void spare_give(int kind, int device, void *ptr, size_t bytes) {
+    if (!ptr) return;
+    SpareBuffer old = {0, 0, nullptr, 0};
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mutex);
+        if (g_spares.size() >= kMaxSpares) { old = g_spares.front(); g_spares.erase(g_spares.begin()); }
+        g_spares.push_back({kind, device, ptr, bytes});
+    }
+    if (old.ptr) spare_release(old);
+}
 }  // namespace lj
 
 extern "C" const char *lj_last_error(void) { return g_error.c_str(); }
@@ -382,13 +418,13 @@ extern "C" void lj_scene_destroy(lj_scene *s) {
     cudaDeviceSynchronize();  // the caller's streams may still read the tables
     for (void *p : s->allocations) lj_dev_free(p);
     if (s->pool_block) pool_block_give(s->device, s->pool_block, s->pool_bytes);
-    if (s->d_film) cudaFree(s->d_film);
-    if (s->d_film_sq) cudaFree(s->d_film_sq);
+    spare_give(kSpareDevice, s->device, s->d_film, s->film_bytes);
+    spare_give(kSpareDevice, s->device, s->d_film_sq, s->film_bytes);
     for (cudaEvent_t e : s->event_pool) cudaEventDestroy(e);
-    if (s->d_counters) cudaFree(s->d_counters);
-    if (s->d_cursors) cudaFree(s->d_cursors);
-    if (s->d_qstack) cudaFree(s->d_qstack);
-    if (s->h_counters) cudaFreeHost(s->h_counters);
+    lj_dev_free(s->d_counters);
+    lj_dev_free(s->d_cursors);
+    lj_dev_free(s->d_qstack);
+    spare_give(kSpareHost, s->device, s->h_counters, s->h_counters_bytes);
     for (auto &e : s->ev) if (e) cudaEventDestroy(e);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;

@@ -30,6 +30,7 @@ struct lj_scene {
     int pool_capacity = 0;
     float *d_film = nullptr;    // w*h*4 fp32: sum rgb, sample count
     float *d_film_sq = nullptr; // w*h*4 fp32: sum of squares rgb
+    size_t film_bytes = 0, h_counters_bytes = 0;
     // reused across renders: event creation / pinned allocation cost ~0.4 s per 1024-spp render otherwise
     std::vector<cudaEvent_t> event_pool;
     unsigned long long *d_counters = nullptr, *h_counters = nullptr;
@@ -77,6 +78,10 @@ struct DeviceGuard {
 // stalls the host for up to 100 ms now and then, which a render-per-scene caller pays on every call.
 void *pool_block_take(int device, size_t bytes, size_t *got_bytes);
 void pool_block_give(int device, void *block, size_t bytes);
+// recycled cudaMalloc (films) / cudaMallocHost (counters) buffers, exact size match; nullptr if the allocation fails
+enum { kSpareDevice = 0, kSpareHost = 1 };
+void *spare_take(int kind, int device, size_t bytes);
+void spare_give(int kind, int device, void *ptr, size_t bytes);
 void set_error(const std::string &msg);
 std::vector<int> init_devices();  // the device list of the last lj_init
 int cuda_fail(cudaError_t e, const char *what);

@@ -1238,7 +1238,7 @@ static int ensure_qstack(lj_scene *s) {
     if (s->d_qstack) return LJ_OK;
     s->qdepth = std::max(4, s->info.bvh_depth + 2);
     size_t bytes = (size_t)s->geom.q_blocks * kQWarps * s->qdepth * kQRays * sizeof(U2);
-    LJ_CUDA(cudaMalloc(&s->d_qstack, bytes));
+    LJ_CUDA(lj_dev_alloc(&s->d_qstack, bytes));
     return LJ_OK;
 }
 
@@ -1297,12 +1297,20 @@ static uint64_t launch_walk_staged(lj_scene *s, const WaveArgs &a, cudaStream_t 
 }
 
 static int ensure_render_buffers(lj_scene *s, int npix, bool want_sq) {
-    if (!s->d_film) LJ_CUDA(cudaMalloc(&s->d_film, (size_t)npix * 16));
-    if (want_sq && !s->d_film_sq) LJ_CUDA(cudaMalloc(&s->d_film_sq, (size_t)npix * 16));
-    if (!s->d_counters) LJ_CUDA(cudaMalloc(&s->d_counters, sizeof(unsigned long long) * C_TOTAL));
-    if (!s->h_counters) LJ_CUDA(cudaMallocHost(&s->h_counters, sizeof(unsigned long long) * (C_TOTAL + 8)));
-    if (!s->d_cursors) LJ_CUDA(cudaMalloc(&s->d_cursors, 4 * sizeof(unsigned int)));
-    return ensure_qstack(s);
+    // films and the pinned counters come from the process-wide spares (scene.cu); the rest from the stream-ordered pool
+    s->film_bytes = (size_t)npix * 16;
+    s->h_counters_bytes = sizeof(unsigned long long) * (C_TOTAL + 8);
+    if (!s->d_film && !(s->d_film = (float *)spare_take(kSpareDevice, s->device, s->film_bytes))) return cuda_fail(cudaErrorMemoryAllocation, "film allocation");
+    if (want_sq && !s->d_film_sq && !(s->d_film_sq = (float *)spare_take(kSpareDevice, s->device, s->film_bytes))) return cuda_fail(cudaErrorMemoryAllocation, "film allocation");
+    const bool fresh = !s->d_counters || !s->d_cursors || !s->d_qstack;
+    if (!s->d_counters) LJ_CUDA(lj_dev_alloc((void **)&s->d_counters, sizeof(unsigned long long) * C_TOTAL));
+    if (!s->h_counters && !(s->h_counters = (unsigned long long *)spare_take(kSpareHost, s->device, s->h_counters_bytes))) return cuda_fail(cudaErrorMemoryAllocation, "pinned counters");
+    if (!s->d_cursors) LJ_CUDA(lj_dev_alloc((void **)&s->d_cursors, 4 * sizeof(unsigned int)));
+    int r = ensure_qstack(s);
+    // (the stream-ordered allocations were made on the default stream and are used on the caller's, which may be a
+    //  non-blocking one: once per scene)
+    if (r == LJ_OK && fresh) LJ_CUDA(cudaStreamSynchronize((cudaStream_t)0));
+    return r;
 }
 
 static int render_impl(lj_scene *s, const lj_render_opts *opts_in, float *d_out, float *d_var, cudaStream_t stream, lj_stats *stats) {
@@ -1339,10 +1347,13 @@ static int render_impl(lj_scene *s, const lj_render_opts *opts_in, float *d_out,
     const int tiles_local = tiles > opts.tile_offset ? (tiles - opts.tile_offset + tile_stride - 1) / tile_stride : 0;
     const unsigned long long total_items = (unsigned long long)tiles_local * 32ull * (unsigned)(se - sb);
     // Pool capacity: a multiple of 256 slots (whole blocks of k_regen, whole warps and sh_mask words everywhere), at
-    // least 1024, and no more slots than there are samples to start.  The default is sized to the work: 4 Mi slots for
+    // least 1024, and no more slots than there are samples to start.  The default is sized to the work: 4 or 8 Mi slots for
     // a full-size render, fewer when the call renders a small share (a rank of a strong-scaling run, a small image),
     // so that short renders do not pay for clearing and sweeping an almost empty pool.
-    long long capacity = opts.pool_paths > 0 ? opts.pool_paths : (1 << 22);
+    // (8 Mi slots for long renders: the persistent traversal kernels lose a fixed ramp-down per launch, and a pool twice
+    //  the size halves its share -- sponza at 1024 spp 203 -> 213 Msamples/s, profiles/r02x_pool.txt; at 128 spp the two
+    //  sizes tie, and larger pools lose to the sweep of an emptying pool at the end of the render)
+    long long capacity = opts.pool_paths > 0 ? opts.pool_paths : (total_items >= (64ull << 20) ? (1 << 23) : (1 << 22));
     if ((unsigned long long)capacity > total_items) capacity = (long long)total_items;
     capacity = std::max<long long>(1024, (capacity + 255) / 256 * 256);
     const Tuning &tune = tuning();
