@@ -49,9 +49,10 @@ def workload_name(key, w, h, full_spp):
     return f"{key} {w}x{h} {'volpath' if key in VOLPATH else 'path'} integrator, {full_spp} spp"
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_trace_q<0> launch (3.9 M rays) from the ncu --set full capture
-# profiles/r02b_sponza_ncu.txt (sponza, steady-state wave); other workloads have no capture of that kernel
-NCU_TRAFFIC_BYTES_PER_LAUNCH = {"sponza": 217.652480e6 + 48.599808e6}
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_trace_q<0> launch per ray it traced, from the ncu --set full
+# capture profiles/r02y_sponza_metrics.txt (sponza, steady-state wave of a 4 Mi-slot pool: 217.6 + 50.4 MB for 3.9 M
+# rays); a launch of the bench's larger pool moves proportionally more.  Other workloads have no capture of that kernel.
+NCU_TRAFFIC_BYTES_PER_RAY = {"sponza": (217.648640e6 + 50.367488e6) / 3.9036e6}
 
 
 def load_peaks():
@@ -205,11 +206,24 @@ def main():
         # 396 Msamples/s at N=2 with NVLS off, = 2 x the single-GPU rate).  An explicit setting in the environment wins.
         os.environ.setdefault("NCCL_NVLS_ENABLE", "0")
         import torch.distributed as dist
+
+    def init_dist():
+        if dist is None:
+            return
         if args.backend == "nccl":
             dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         else:
             dist.init_process_group("gloo")
 
+    # Order matters (measured, profiles/r02z4_nccl.txt): device memory allocated AFTER the NCCL communicator exists makes
+    # the random-access traversal kernel 8-15 % slower (k_trace_q<0>: 586 -> 630..680 ms per 512 spp, whatever the NCCL
+    # transport settings; shade / shadow / regen unaffected), memory allocated before it does not.  So the scene, the
+    # path pool and the traversal scratch are allocated -- one untimed render of this rank's share -- before
+    # init_process_group, the way an application loads its scene before it sets up communication.  The later scenes of
+    # the e2e leg reuse those blocks (the library recycles them).  LJ_BENCH_EARLY_DIST=1 restores the other order (A/B).
+    early = os.environ.get("LJ_BENCH_EARLY_DIST") == "1"
+    if early:
+        init_dist()
     key, full_spp, cpu_spp = WORKLOADS[args.workload]
     spp = args.spp or full_spp
     ljs_path, _ = scene_paths(args.workload)
@@ -247,6 +261,12 @@ def main():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
+
+    if not early and dist is not None:
+        scene.render_device(film.data_ptr(), stream.cuda_stream, spp=total_spp, sample_begin=s_begin, sample_end=s_end, normalize=False,
+                            pool_paths=args.pool, tile_stride=tile_stride, tile_offset=tile_offset)
+        torch.cuda.synchronize()
+        init_dist()
 
     for _ in range(args.warmup):
         step()
@@ -331,8 +351,9 @@ def main():
                     "d2h_bytes_per_step": int(npix * 3 * 4), "includes": "lj_scene_create (upload + GPU BVH/mip build) + lj_render + D2H", "parts": e2e_parts},
             "gpu_launches": int(agg["launches"]),
             "roofline": {"bound": "hbm", "kernel": "k_trace_q<0> (closest-hit extension)" if key not in VOLPATH else "k_trace<0> (closest-hit extension)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH.get(key) if spp == full_spp else None,
-                         "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r02b_sponza_ncu.txt)", "peak_kind": peak_kind,
+                         "frac": achieved / peak,
+                         "traffic": NCU_TRAFFIC_BYTES_PER_RAY[key] * agg["closest"] / max(agg["extend_launches"], 1) if key in NCU_TRAFFIC_BYTES_PER_RAY else None,
+                         "traffic_unit": "bytes per launch: ncu dram read+write per ray (profiles/r02y_sponza_metrics.txt) x rays per launch of this run", "peak_kind": peak_kind,
                          "algorithmic_bytes_per_ray": BYTES_PER_EXTENSION_RAY,
                          "rays_per_launch": agg["closest"] / max(agg["extend_launches"], 1),
                          "avg_launch_ms": agg["extend_ms"] / max(agg["extend_launches"], 1)},

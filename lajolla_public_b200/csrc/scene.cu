@@ -423,7 +423,7 @@ extern "C" void lj_scene_destroy(lj_scene *s) {
     for (cudaEvent_t e : s->event_pool) cudaEventDestroy(e);
     lj_dev_free(s->d_counters);
     lj_dev_free(s->d_cursors);
-    lj_dev_free(s->d_qstack);
+    spare_give(kSpareDevice, s->device, s->d_qstack, s->qstack_bytes);
     spare_give(kSpareHost, s->device, s->h_counters, s->h_counters_bytes);
     for (auto &e : s->ev) if (e) cudaEventDestroy(e);
     if (s->stream) cudaStreamDestroy(s->stream);

@@ -30,7 +30,7 @@ struct lj_scene {
     int pool_capacity = 0;
     float *d_film = nullptr;    // w*h*4 fp32: sum rgb, sample count
     float *d_film_sq = nullptr; // w*h*4 fp32: sum of squares rgb
-    size_t film_bytes = 0, h_counters_bytes = 0;
+    size_t film_bytes = 0, h_counters_bytes = 0, qstack_bytes = 0;
     // reused across renders: event creation / pinned allocation cost ~0.4 s per 1024-spp render otherwise
     std::vector<cudaEvent_t> event_pool;
     unsigned long long *d_counters = nullptr, *h_counters = nullptr;

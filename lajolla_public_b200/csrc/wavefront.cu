@@ -2,14 +2,15 @@
 // pool of path records resident in HBM, and the render entry points of the C ABI.
 // Replaces the reference's tile thread pool (render.cpp:71-152, parallel.cpp) and the per-sample
 // control flow of path_tracing.h.  Stage kernels:
-//   k_regen   K1+K7  flush finished paths to the film, start new camera paths in free slots
-//   k_trace<0> K2    persistent threads, closest-hit traversal for every live path
-//   k_shade    K4    emission+MIS, Russian roulette, NEE sample, BSDF sample (lj_path.h)
-//   k_trace<1> K3    persistent threads, any-hit traversal of the NEE shadow rays
-// Path records are addressed by slot = thread index in regen/shade (fully coalesced 16-byte records);
-// the pool is kept dense by regenerating finished paths in place rather than by index queues --
-// measured: index queues made k_shade 2x slower through uncoalesced record access
-// (profiles/r01_b_*).
+//   k_regen      K1+K7  flush finished paths to the film, start new camera paths in free slots
+//   k_trace_q<0> K2     persistent, queue form: closest-hit traversal for every live path (volpath: k_trace<0>)
+//   k_shade      K4     emission+MIS, Russian roulette, NEE sample, BSDF sample (lj_path.h); k_flight + k_shade_vol for volpath
+//   k_trace_q<1> K3     persistent: any-hit traversal of the NEE shadow rays (volpath: the NEE walk, k_trace<2> or staged)
+// Path records are addressed by slot = thread index in regen and in the first shade pass (fully coalesced 16-byte
+// records); the pool is kept dense by regenerating finished paths in place.  A general index queue in front of k_shade
+// made it 2x slower through uncoalesced record access (profiles/r01_b_*), so queues are used only where the code behind
+// them is expensive and sparse: the Disney pass of k_shade and the surface pass of k_shade_vol gather their records
+// through pool.class_queue (profiles/r02l_* -> r02m_*).
 #include "scene.cuh"
 #include "lj_volpath.h"
 
@@ -1238,7 +1239,10 @@ static int ensure_qstack(lj_scene *s) {
     if (s->d_qstack) return LJ_OK;
     s->qdepth = std::max(4, s->info.bvh_depth + 2);
     size_t bytes = (size_t)s->geom.q_blocks * kQWarps * s->qdepth * kQRays * sizeof(U2);
-    LJ_CUDA(lj_dev_alloc(&s->d_qstack, bytes));
+    // (plain cudaMalloc memory, recycled through the spares of scene.cu: the kernel's hottest global buffer stays out
+    //  of the stream-ordered pool, whose mappings a host process's NCCL may widen to its peers)
+    s->qstack_bytes = bytes;
+    if (!(s->d_qstack = spare_take(kSpareDevice, s->device, bytes))) return cuda_fail(cudaErrorMemoryAllocation, "traversal scratch allocation");
     return LJ_OK;
 }
 
