@@ -308,6 +308,14 @@ typedef struct lj_medium_query { float org[3], tfar, dir[3], t, rnd[2]; int32_t 
 typedef struct lj_medium_result { float majorant[3], sigma_a[3], sigma_s[3], phase_dir[3], phase_eval, phase_pdf; } lj_medium_result;
 int lj_medium_batch(lj_scene *scene, const lj_medium_query *q, int64_t n, lj_medium_result *out);
 
+/* The bound the tracking loops actually use at the point org + t * dir of medium `medium_id` (lj_media.h): a grid medium is
+ * bounded block by block by its majorant grid where the reference uses the global maximum of get_majorant (medium.cpp:27-29).
+ *   majorant = the block's bound (common to the three channels), t_exit = the ray parameter at which it stops holding,
+ *   sigma_t  = sigma_a + sigma_s at the point (what the bound must dominate), local = 0 if the medium has no majorant grid
+ * (then majorant is the global one and t_exit is infinite). */
+typedef struct lj_medium_bound { float majorant[3], t_exit, sigma_t[3]; int32_t local; } lj_medium_bound;
+int lj_medium_bound_batch(lj_scene *scene, const lj_medium_query *q, int64_t n, lj_medium_bound *out);
+
 /* sample_primary (camera.cpp:23-47): screen_pos (x,y in [0,1]^2) -> ray. */
 int lj_camera_rays(lj_scene *scene, const float *screen_pos_xy, int64_t n, lj_ray *rays);
 

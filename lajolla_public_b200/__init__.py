@@ -46,6 +46,8 @@ assert LIGHT_QUERY_DTYPE.itemsize == C.sizeof(abi.lj_light_query)
 assert LIGHT_RESULT_DTYPE.itemsize == C.sizeof(abi.lj_light_result)
 assert MEDIUM_QUERY_DTYPE.itemsize == C.sizeof(abi.lj_medium_query)
 assert MEDIUM_RESULT_DTYPE.itemsize == C.sizeof(abi.lj_medium_result)
+MEDIUM_BOUND_DTYPE = np.dtype([("majorant", "<f4", 3), ("t_exit", "<f4"), ("sigma_t", "<f4", 3), ("local", "<i4")])
+assert MEDIUM_BOUND_DTYPE.itemsize == C.sizeof(abi.lj_medium_bound)
 assert WALK_QUERY_DTYPE.itemsize == C.sizeof(abi.lj_walk_query)
 
 
@@ -166,6 +168,14 @@ class Scene:
         q = np.ascontiguousarray(queries, dtype=MEDIUM_QUERY_DTYPE)
         out = np.zeros(q.shape[0], dtype=MEDIUM_RESULT_DTYPE)
         abi.check(self._lib.lj_medium_batch(self._h, _ptr(q, abi.lj_medium_query), q.shape[0], _ptr(out, abi.lj_medium_result)))
+        return out
+
+    def medium_bounds(self, queries):
+        """The bound the tracking loops use at org + t * dir (block-wise majorant of a grid medium), where it stops
+        holding, and sigma_t at the point."""
+        q = np.ascontiguousarray(queries, dtype=MEDIUM_QUERY_DTYPE)
+        out = np.zeros(q.shape[0], dtype=MEDIUM_BOUND_DTYPE)
+        abi.check(self._lib.lj_medium_bound_batch(self._h, _ptr(q, abi.lj_medium_query), q.shape[0], _ptr(out, abi.lj_medium_bound)))
         return out
 
     def nee_walks(self, queries, kernel=abi.LJ_TRACE_PLAIN, pool_paths=0, slot_stride=1, want_ms=False):

@@ -135,6 +135,10 @@ class lj_medium_result(C.Structure):
                 ("phase_eval", f32), ("phase_pdf", f32)]
 
 
+class lj_medium_bound(C.Structure):
+    _fields_ = [("majorant", f32 * 3), ("t_exit", f32), ("sigma_t", f32 * 3), ("local", i32)]
+
+
 class lj_light_result(C.Structure):
     _fields_ = [("light_id", i32), ("position", f32 * 3), ("normal", f32 * 3), ("pmf", f32), ("pdf", f32),
                 ("emission", f32 * 3)]
@@ -164,6 +168,7 @@ PROTOTYPES = {
     "lj_bsdf_batch": (C.c_int, [C.c_void_p, C.POINTER(lj_bsdf_query), i64, C.POINTER(lj_bsdf_result)]),
     "lj_light_batch": (C.c_int, [C.c_void_p, C.POINTER(lj_light_query), i64, C.POINTER(lj_light_result)]),
     "lj_medium_batch": (C.c_int, [C.c_void_p, C.POINTER(lj_medium_query), i64, C.POINTER(lj_medium_result)]),
+    "lj_medium_bound_batch": (C.c_int, [C.c_void_p, C.POINTER(lj_medium_query), i64, C.POINTER(lj_medium_bound)]),
     "lj_camera_rays": (C.c_int, [C.c_void_p, pf32, i64, C.POINTER(lj_ray)]),
     "lj_texture_batch": (C.c_int, [C.c_void_p, i32, i32, pf32, i64, pf32]),
     "lj_pcg32_batch": (C.c_int, [u64, u64, i32, i32, C.POINTER(u32), pf32]),

@@ -118,6 +118,24 @@ __global__ void __launch_bounds__(128) k_medium(const LJ_GRID_CONSTANT DevScene 
     out[i] = r;
 }
 
+__global__ void __launch_bounds__(128) k_medium_bound(const LJ_GRID_CONSTANT DevScene sc, const lj_medium_query *q, long long n, lj_medium_bound *out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    lj_medium_query in = q[i];
+    const DevMedium &m = sc.media[in.medium_id];
+    V3 o = v3_in(in.org), d = v3_in(in.dir);
+    lj_medium_bound r;
+    r.local = medium_has_local_majorant(m) ? 1 : 0;
+    if (r.local) {
+        v3_out(r.majorant, volume_block_majorant(m.density, o, d, in.t, r.t_exit));
+    } else {
+        v3_out(r.majorant, medium_majorant(m, o, d, in.tfar));
+        r.t_exit = LJ_INF;
+    }
+    v3_out(r.sigma_t, medium_sigma_t(m, o + d * in.t));
+    out[i] = r;
+}
+
 __global__ void __launch_bounds__(128) k_light(const LJ_GRID_CONSTANT DevScene sc, const lj_light_query *q, long long n, lj_light_result *out) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -275,6 +293,22 @@ extern "C" int lj_medium_batch(lj_scene *s, const lj_medium_query *q, int64_t n,
     LJ_CUDA(dq.err); LJ_CUDA(dr.err);
     LJ_CUDA(dq.up(q, n));
     LJ_LAUNCH(k_medium, grid_for(n, 128), 128, s->stream, s->dev, dq.p, n, dr.p);
+    LJ_CUDA(cudaStreamSynchronize(s->stream));
+    LJ_CUDA(cudaGetLastError());
+    LJ_CUDA(dr.down(out, n));
+    return LJ_OK;
+}
+
+extern "C" int lj_medium_bound_batch(lj_scene *s, const lj_medium_query *q, int64_t n, lj_medium_bound *out) {
+    LJ_CHECK_ARGS(s && q && out && n >= 0);
+    DeviceGuard guard(s->device);
+    if (n == 0) return LJ_OK;
+    for (int64_t i = 0; i < n; i++)
+        if (q[i].medium_id < 0 || q[i].medium_id >= s->dev.num_media) { set_error("medium id out of range"); return LJ_ERR_INVALID; }
+    DevBuf<lj_medium_query> dq(n); DevBuf<lj_medium_bound> dr(n);
+    LJ_CUDA(dq.err); LJ_CUDA(dr.err);
+    LJ_CUDA(dq.up(q, n));
+    LJ_LAUNCH(k_medium_bound, grid_for(n, 128), 128, s->stream, s->dev, dq.p, n, dr.p);
     LJ_CUDA(cudaStreamSynchronize(s->stream));
     LJ_CUDA(cudaGetLastError());
     LJ_CUDA(dr.down(out, n));

@@ -355,6 +355,57 @@ def image_stats(img, ref_img, var=None, ref_var=None, block=8):
     return out
 
 
+def check_block_majorants(scene, n=4000, seed=9, max_blocks=400):
+    """The block-wise majorants of the tracking loops (lj_media.h, lj_medium_bound_batch) are a valid bound: along random
+    rays through every grid medium, walked block by block the way flight_step / ratio_step walk them,
+      * t_exit is strictly ahead of t and the walk leaves the grid box after a bounded number of blocks,
+      * sigma_t at random points of [t, t_exit) never exceeds the block's majorant (all three channels),
+      * the majorant never exceeds the medium's global one (get_majorant, medium.cpp:27-29)."""
+    rng = np.random.default_rng(seed)
+    out = {}
+    for mid, m in enumerate(scene.desc.media):
+        if not m.density.is_grid:
+            continue
+        lo, hi = np.array(m.density.p_min, dtype=np.float64), np.array(m.density.p_max, dtype=np.float64)
+        org = (lo + (hi - lo) * rng.uniform(-0.3, 1.3, (n, 3))).astype(np.float32)
+        tgt = lo + (hi - lo) * rng.uniform(0.0, 1.0, (n, 3))
+        d = tgt - org
+        d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+        q = np.zeros(n, dtype=lj.MEDIUM_QUERY_DTYPE)
+        q["org"], q["dir"], q["tfar"], q["medium_id"] = org, d, np.inf, mid
+        glob = scene.medium(q)["majorant"]
+        t = np.zeros(n, dtype=np.float32)
+        alive = np.ones(n, dtype=bool)
+        worst, blocks, inside_blocks = 0.0, 0, 0
+        for _ in range(max_blocks):
+            if not alive.any():
+                break
+            qa = q[alive].copy()
+            qa["t"] = t[alive]
+            b = scene.medium_bounds(qa)
+            assert np.all(b["local"] == 1)
+            assert np.all(b["t_exit"] > qa["t"]), "a block step that does not advance"
+            assert np.all(b["majorant"] <= glob[alive] * (1 + 1e-5) + 1e-12), "block majorant above the global one"
+            fin = np.isfinite(b["t_exit"])
+            # sigma_t at random points of the block's stretch of the ray
+            for _k in range(3):
+                u = rng.random(len(qa)).astype(np.float32)
+                qs = qa[fin].copy()
+                qs["t"] = qa["t"][fin] + u[fin] * (b["t_exit"][fin] - qa["t"][fin]) * np.float32(0.999)
+                bs = scene.medium_bounds(qs)
+                excess = (bs["sigma_t"] - b["majorant"][fin]).max() if len(qs) else 0.0
+                worst = max(worst, float(excess))
+            inside_blocks += int((b["majorant"].max(axis=1) > 0).sum())
+            blocks += len(qa)
+            idx = np.nonzero(alive)[0]
+            t[idx] = b["t_exit"]
+            alive[idx[~fin]] = False
+        assert not alive.any(), f"{int(alive.sum())} rays still inside the grid after {max_blocks} blocks"
+        assert worst <= 0.0, f"sigma_t exceeds the block majorant by {worst}"
+        out[f"medium{mid}"] = dict(rays=int(n), block_steps=int(blocks), nonempty_block_steps=int(inside_blocks))
+    return out
+
+
 def check_medium_parity(scene, ref, n=20000, seed=6):
     """get_majorant / get_sigma_a / get_sigma_s (medium.cpp:27-37, volume.h:45-81,125-144) and the phase function
     (phase_functions/*.inl) on points in and around each medium's grid box."""

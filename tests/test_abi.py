@@ -31,7 +31,8 @@ def test_library_exports_every_declared_symbol():
 def test_struct_sizes_match_the_header(tmp_path):
     structs = ["lj_image_desc", "lj_texture_desc", "lj_material_desc", "lj_shape_desc", "lj_light_desc", "lj_volume_desc",
                "lj_medium_desc", "lj_camera_desc", "lj_options_desc", "lj_scene_desc", "lj_render_opts", "lj_stats", "lj_ray",
-               "lj_hit", "lj_vertex", "lj_bsdf_query", "lj_bsdf_result", "lj_light_query", "lj_light_result", "lj_scene_info"]
+               "lj_hit", "lj_vertex", "lj_bsdf_query", "lj_bsdf_result", "lj_light_query", "lj_light_result", "lj_scene_info",
+               "lj_medium_query", "lj_medium_result", "lj_medium_bound", "lj_walk_query", "lj_trace_opts"]
     prog = '#include <stdio.h>\n#include "lajolla_b200.h"\nint main(void){' + "".join(
         f'printf("{s} %zu\\n", sizeof({s}));' for s in structs) + "return 0;}"
     c = tmp_path / "sizes.c"

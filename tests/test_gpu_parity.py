@@ -235,6 +235,14 @@ def test_image_parity_homework_configs(oracle, name, spp):
     assert s["block_z_rms"] <= 1.15 * null["block_z_rms"] + 0.02, (s, null)
 
 
+@pytest.mark.parametrize("name", ["hetvol", "hetvol_colored"])
+def test_block_majorants_bound_the_medium(oracle, name):
+    sc, _ = pair(oracle, name)
+    r = pc.check_block_majorants(sc)
+    assert r, "scene has no grid medium"
+    record("block_majorants", dict(scene=name, **r))
+
+
 @pytest.mark.parametrize("name,spp", [("hetvol", 32), ("hetvol_colored", 32)])
 def test_local_majorants_keep_the_expectation(oracle, name, spp):
     """The tracking loops bound a grid medium block by block (lj_media.h) where the reference uses one global majorant

@@ -132,6 +132,13 @@ def test_medium_parity(oracle, name):
     pc.check_medium_parity(sc, ref, n=5000)
 
 
+@pytest.mark.parametrize("name", ["hetvol", "hetvol_colored"])
+def test_block_majorants_bound_the_medium(oracle, name):
+    """The majorant grid of the tracking loops really bounds the density (host build of the device code)."""
+    sc, _ = pair(oracle, name)
+    assert pc.check_block_majorants(sc, n=600)
+
+
 def test_light_parity_facing_the_pole(oracle):
     """Sphere-light cone sampling builds a frame around the direction to the light's centre; for directions
     close to -z the reference's frame (frame.h:6-17) needs 1 / (1 + n.z), which fp32 can only get from the
