@@ -484,7 +484,7 @@ LJ_HD bool disney_bsdf_sample(const DisneyParams &p, const Vertex &vx, V3 wi, V2
 // kMatDisney (the six Disney alternatives).  Scenes with Disney materials shade in two passes, one kernel per class
 // (wavefront.cu): the Disney lobes are ~10x the code of the small materials, and a kernel that holds both spends its
 // time waiting for instructions (60 % of the stall samples "no instruction", profiles/r02g_disney_shade_ncu.txt).
-enum { kMatAll = 0, kMatSmall = 1, kMatDisney = 2 };
+enum { kMatAll = 0, kMatSmall = 1, kMatDisney = 2, kMatLambert = 3 /* scenes whose every material is Lambertian: shade_path only */ };
 LJ_HD bool material_is_disney(int type) { return type >= LJ_MAT_DISNEY_DIFFUSE; }
 
 // A material at one vertex.  For the principled BSDF the twelve parameter textures are evaluated ONCE here instead of

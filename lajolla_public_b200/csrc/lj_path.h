@@ -132,6 +132,7 @@ LJ_HD int path_material_class(const DevScene &sc, int prim) {
 template <int CLASS>
 LJ_HD void shade_path(const DevScene &sc, const RenderParams &rp, PathState &s, ShadeCounters &cnt) {
     constexpr bool CALLS = CLASS == kMatDisney;
+    constexpr int DISPATCH = CLASS == kMatLambert ? kMatSmall : CLASS;  // (dead code in the Lambertian-only kernel)
     Pcg rng = path_rng(s, rp);
     const bool primary = s.pdf_sa < 0;
     s.sh_tfar = -1;
@@ -195,9 +196,12 @@ LJ_HD void shade_path(const DevScene &sc, const RenderParams &rp, PathState &s, 
     const DevMaterial &mat = sc.materials[vx.material_id];
     // Lambertian fast path: the reflectance texture is fetched once per vertex instead of once per eval() call
     // (material.cpp evaluates it inside each of eval / pdf / sample; same values, lambertian.inl:1-50)
-    const bool lambert = CLASS != kMatDisney && mat.type == LJ_MAT_LAMBERTIAN;
+    // (CLASS == kMatLambert: the host checked that the scene has no other material -- the dispatchers are compiled out)
+    const bool lambert = CLASS == kMatLambert || (CLASS != kMatDisney && mat.type == LJ_MAT_LAMBERTIAN);
     const V3 lambert_R = lambert ? mat_tex3(sc, mat, 0, vx) : mk3(0);
-    const MatCtx mc = mat_ctx<CLASS>(sc, mat, vx);
+    MatCtx mc;
+    mc.m = &mat;
+    if (CLASS != kMatLambert) mc = mat_ctx<CLASS>(sc, mat, vx);
 
     // ---- next event estimation, :94-207
     float lu = pcg_uniform(rng), lv = pcg_uniform(rng);
@@ -221,10 +225,10 @@ LJ_HD void shade_path(const DevScene &sc, const RenderParams &rp, PathState &s, 
         float p1 = light_pmf(sc, light_id) * pdf_point_on_light(sc, light, pl, vx.position);
         if (G > 0 && p1 > 0) {
             V3 f = lambert ? lambertian_eval(lambert_R, vx, dir_view, dir_light)
-                           : (CALLS ? bsdf_eval_call(sc, mc, dir_view, dir_light, vx, 0) : bsdf_eval<CLASS>(sc, mc, dir_view, dir_light, vx, 0));
+                           : (CALLS ? bsdf_eval_call(sc, mc, dir_view, dir_light, vx, 0) : bsdf_eval<DISPATCH>(sc, mc, dir_view, dir_light, vx, 0));
             V3 Le = light_emission(sc, light, -dir_light, 0.f, pl);
             float p2 = (lambert ? lambertian_pdf(vx, dir_view, dir_light)
-                                : (CALLS ? bsdf_pdf_call(sc, mc, dir_view, dir_light, vx) : bsdf_pdf<CLASS>(sc, mc, dir_view, dir_light, vx))) * G;
+                                : (CALLS ? bsdf_pdf_call(sc, mc, dir_view, dir_light, vx) : bsdf_pdf<DISPATCH>(sc, mc, dir_view, dir_light, vx))) * G;
             float w1 = mis_power(p1, p2);
             V3 c = s.T * (f * Le) * (G / p1 * w1);
             if (max3(c) > 0 || min3(c) < 0 || c.x != c.x || c.y != c.y || c.z != c.z) {
@@ -241,7 +245,7 @@ LJ_HD void shade_path(const DevScene &sc, const RenderParams &rp, PathState &s, 
     s.rng_state = rng.state;
     BsdfSample bs;
     if (!(lambert ? lambertian_sample(vx, dir_view, mk2(bu, bv), bs)
-                  : (CALLS ? bsdf_sample_call(sc, mc, dir_view, vx, mk2(bu, bv), bw, bs) : bsdf_sample<CLASS>(sc, mc, dir_view, vx, mk2(bu, bv), bw, bs)))) { cnt.finished++; return; }
+                  : (CALLS ? bsdf_sample_call(sc, mc, dir_view, vx, mk2(bu, bv), bw, bs) : bsdf_sample<DISPATCH>(sc, mc, dir_view, vx, mk2(bu, bv), bw, bs)))) { cnt.finished++; return; }
     // ray_diff.radius stays 0 for the whole path upstream (only .spread is updated, :227-230)
     if (bs.eta == 0) {
         s.spread = spread_reflect(0.f, s.spread, vx.mean_curvature, bs.roughness);
@@ -250,9 +254,9 @@ LJ_HD void shade_path(const DevScene &sc, const RenderParams &rp, PathState &s, 
         s.eta_scale /= (bs.eta * bs.eta);
     }
     V3 f = lambert ? lambertian_eval(lambert_R, vx, dir_view, bs.dir_out)
-                   : (CALLS ? bsdf_eval_call(sc, mc, dir_view, bs.dir_out, vx, 0) : bsdf_eval<CLASS>(sc, mc, dir_view, bs.dir_out, vx, 0));
+                   : (CALLS ? bsdf_eval_call(sc, mc, dir_view, bs.dir_out, vx, 0) : bsdf_eval<DISPATCH>(sc, mc, dir_view, bs.dir_out, vx, 0));
     float p2 = lambert ? lambertian_pdf(vx, dir_view, bs.dir_out)
-                       : (CALLS ? bsdf_pdf_call(sc, mc, dir_view, bs.dir_out, vx) : bsdf_pdf<CLASS>(sc, mc, dir_view, bs.dir_out, vx));
+                       : (CALLS ? bsdf_pdf_call(sc, mc, dir_view, bs.dir_out, vx) : bsdf_pdf<DISPATCH>(sc, mc, dir_view, bs.dir_out, vx));
     if (!(p2 > 0)) { cnt.finished++; return; }
     s.rr_prob = fminf(max3(s.T) / s.eta_scale, 0.95f);  // :313, evaluated with the pre-update throughput
     s.T = s.T * f / p2;

@@ -755,6 +755,8 @@ static int scene_create_here(const lj_scene_desc *desc, lj_scene **out) {
         }
     }
     for (int i = 0; i < desc->num_materials; i++) if (desc->materials[i].type >= LJ_MAT_DISNEY_DIFFUSE) s->has_disney = true;
+    s->only_lambertian = desc->num_materials > 0;
+    for (int i = 0; i < desc->num_materials; i++) if (desc->materials[i].type != LJ_MAT_LAMBERTIAN) s->only_lambertian = false;
     sc.media = up.upload(media);
     sc.num_media = desc->num_media;
     if (up.err != cudaSuccess) { int r = cuda_fail(up.err, "table upload"); lj_scene_destroy(s); return r; }

@@ -18,6 +18,7 @@ struct lj_scene {
     std::vector<void *> allocations;  // everything cudaMalloc'ed for this scene
     lj_scene_info info;
     int device = 0;
+    bool only_lambertian = false; // every material is Lambertian: k_shade without the material dispatchers
     bool has_disney = false;      // some material is a Disney lobe: k_shade calls the BSDF dispatchers out of line
     bool has_grid_media = false;  // some medium is heterogeneous: tracking loops run ~100 collisions per segment
     // host copies needed by introspection entry points

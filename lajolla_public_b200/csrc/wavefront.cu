@@ -688,6 +688,12 @@ __global__ void __launch_bounds__(kQWarps * LJ_WARP_WIDTH, 8) k_trace_q(const LJ
 // material-sorted shading of north_star at class granularity.  (Before the queue the second pass ran one thread per
 // slot: 9 of 32 lanes held a Disney vertex on disney_bsdf, profiles/r02l_disney_*.)  The records stay where they are;
 // the second pass gathers them through the queue.  The first pass writes the sh_mask words, the second ORs its bits in.
+// Scenes whose every material is Lambertian (cbox, sponza) shade with k_shade<.., kMatLambert>: the dispatchers of the other
+// materials are compiled out (0.54 MB -> 0.14 MB of SASS, 96 registers at 5 resident CTAs per SM without spills): sponza
+// shade stage 131 -> 111 ms per 256 spp, cbox 45 -> 38 (profiles/r02za_lambert.txt; 6 CTAs spill and gain nothing more).
+#ifndef LJ_LAMBERT_MIN_BLOCKS
+#define LJ_LAMBERT_MIN_BLOCKS 5
+#endif
 constexpr int kCursorClass = 3;  // WaveArgs::cursors[3]: entries in pool.class_queue (path integrator only)
 template <int MIN_BLOCKS, int CLASS>
 __global__ void __launch_bounds__(128, MIN_BLOCKS) k_shade(const LJ_GRID_CONSTANT DevScene sc, const LJ_GRID_CONSTANT WaveArgs a, int split_classes) {
@@ -1164,6 +1170,7 @@ struct EventPool {  // hands out the scene's events in order; they live until lj
 struct Tuning {
     int prim_min_lanes = kPrimMinLanes, refill = kRefillThreshold, track_refill = 24, shadow_chunk = 128, trav_min = 4, chunk = 64;
     int trace_kernel = 1, q_refill = 48, q_chunk = 128;
+    int lambert_kernel = 1;  // scenes with Lambertian materials only: k_shade<.., kMatLambert> (0: the general kernel, A/B)
     int walk_kernel = 1;  // volpath NEE walk: 0 = k_trace<2|3> (one lane per walk), 1 = staged kernels for grid media, 2 = staged for every scene
     int q_blocks = 0, q_carveout = -1;  // resident CTAs of k_trace_q per SM (0: what fits), shared-memory carve-out in % (-1: the maximum)
     bool host_prof = false;
@@ -1182,6 +1189,7 @@ static const Tuning &tuning() {
         geti("LJ_CHUNK", v.chunk, 32, 1 << 16);
         geti("LJ_TRACE_KERNEL", v.trace_kernel, 0, 1);
         geti("LJ_WALK_KERNEL", v.walk_kernel, 0, 2);
+        geti("LJ_LAMBERT_KERNEL", v.lambert_kernel, 0, 1);
         geti("LJ_Q_REFILL", v.q_refill, 1, kQRays);
         geti("LJ_Q_CHUNK", v.q_chunk, kQRays, 1 << 16);
         geti("LJ_Q_BLOCKS", v.q_blocks, 0, 32);
@@ -1444,8 +1452,12 @@ static int render_impl(lj_scene *s, const lj_render_opts *opts_in, float *d_out,
         } else {
             // one pass per material class; the classes are disjoint and a path's class is read from its hit record,
             // which the shade passes do not modify: every live path is shaded exactly once per wave
-            LJ_LAUNCH((k_shade<4, kMatSmall>), nb128, 128, stream, sc, a, s->has_disney ? 1 : 0);
-            if (s->has_disney) { LJ_LAUNCH((k_shade<4, kMatDisney>), nb128, 128, stream, sc, a, 1); launches++; }
+            if (s->only_lambertian && tune.lambert_kernel) {
+                LJ_LAUNCH((k_shade<LJ_LAMBERT_MIN_BLOCKS, kMatLambert>), nb128, 128, stream, sc, a, 0);
+            } else {
+                LJ_LAUNCH((k_shade<4, kMatSmall>), nb128, 128, stream, sc, a, s->has_disney ? 1 : 0);
+                if (s->has_disney) { LJ_LAUNCH((k_shade<4, kMatDisney>), nb128, 128, stream, sc, a, 1); launches++; }
+            }
         }
         LJ_CUDA(cudaEventRecord(e3, stream));
         if (vol && walk_staged(s)) launches += launch_walk_staged(s, a, stream) - 1;
