@@ -91,17 +91,19 @@ LJ_HD bool hit_prim(const DevPrim *prims, int i, V3 o, V3 d, float tnear, float 
     return hit_triangle(xyz(a), mk3(a.w, b.x, b.y), mk3(b.z, b.w, c.x), o, d, tnear, tfar, t);
 }
 // barycentrics of the final hit (spheres carry none: their (u, v) come from the hit point, lj_shapes.h)
-LJ_HD void prim_uv(const DevPrim *prims, int i, V3 o, V3 d, float &u, float &v) {
-    V4 a = ld4(&prims[i].a), b = ld4(&prims[i].b), c = ld4(&prims[i].c);
+LJ_HD void prim_uv(const V4 &a, const V4 &b, const V4 &c, V3 o, V3 d, float &u, float &v) {
     u = 0; v = 0;
     if (!prim_is_sphere(c)) triangle_uv(xyz(a), mk3(a.w, b.x, b.y), mk3(b.z, b.w, c.x), o, d, u, v);
+}
+LJ_HD void prim_uv(const DevPrim *prims, int i, V3 o, V3 d, float &u, float &v) {
+    V4 a = ld4(&prims[i].a), b = ld4(&prims[i].b), c = ld4(&prims[i].c);
+    prim_uv(a, b, c, o, d, u, v);
 }
 
 // Once the closest primitive is known its t is re-evaluated in fp64 on the same fp32 inputs: a grazing
 // ray makes the fp32 quotient dot(v0,Ng)/dot(Ng,d) lose half its digits, and the reference's double
 // shading code consumes that t (intersection.cpp:39-40).  One evaluation per ray, not per candidate.
-LJ_HD float refine_hit_t(const DevPrim *prims, int prim, V3 o, V3 d, float t32) {
-    V4 a = ld4(&prims[prim].a), b = ld4(&prims[prim].b), c = ld4(&prims[prim].c);
+LJ_HD float refine_hit_t(const V4 &a, const V4 &b, const V4 &c, V3 o, V3 d, float t32) {
     double ox = o.x, oy = o.y, oz = o.z, dx = d.x, dy = d.y, dz = d.z;
     if (prim_is_sphere(c)) {
         double fx = ox - a.x, fy = oy - a.y, fz = oz - a.z, r = a.w;
@@ -122,6 +124,11 @@ LJ_HD float refine_hit_t(const DevPrim *prims, int prim, V3 o, V3 d, float t32) 
     double den = nx * dx + ny * dy + nz * dz;
     if (den == 0) return t32;
     return (float)((v0x * nx + v0y * ny + v0z * nz) / den);
+}
+
+LJ_HD float refine_hit_t(const DevPrim *prims, int prim, V3 o, V3 d, float t32) {
+    V4 a = ld4(&prims[prim].a), b = ld4(&prims[prim].b), c = ld4(&prims[prim].c);
+    return refine_hit_t(a, b, c, o, d, t32);
 }
 
 // Stack traversal of the 8-wide compressed BVH (DevNode8, lj_scene_dev.h), after Ylitie, Karras &
@@ -344,8 +351,11 @@ LJ_HD void trav_terminate(Trav &tr) { tr.G.y = 0; tr.Gt.y = 0; tr.sp = 0; }
 // Closest hit: the winning primitive's t is refined in fp64 (see refine_hit_t).
 LJ_HD void trav_finish_closest(const DevPrim *prims, Trav &tr) {
     if (tr.hit.prim == kNoHit) return;
-    prim_uv(prims, tr.hit.prim, tr.o, tr.d, tr.hit.u, tr.hit.v);
-    tr.hit.t = refine_hit_t(prims, tr.hit.prim, tr.o, tr.d, tr.hit.t);
+    // (the winner's three records are fetched once for both: the two helpers loaded them separately and the compiler kept
+    //  both sets of loads -- 3 % of the closest-hit kernel's global-load requests, profiles/r02k per-line counts)
+    const V4 a = ld4(&prims[tr.hit.prim].a), b = ld4(&prims[tr.hit.prim].b), c = ld4(&prims[tr.hit.prim].c);
+    prim_uv(a, b, c, tr.o, tr.d, tr.hit.u, tr.hit.v);
+    tr.hit.t = refine_hit_t(a, b, c, tr.o, tr.d, tr.hit.t);
 }
 
 // Plain single-ray loop (query seam S2 and shading-side helpers).

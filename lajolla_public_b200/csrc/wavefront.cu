@@ -1437,7 +1437,9 @@ static int render_impl(lj_scene *s, const lj_render_opts *opts_in, float *d_out,
             if (h_active[wv % kRing] == 0) { waves = wv; marks.push_back(e0); marks.push_back(e1); marks.push_back(nullptr); break; }
         }
         LJ_CUDA(cudaMemsetAsync(d_cursors, 0, 4 * sizeof(unsigned int), stream));
-        if (vol) LJ_LAUNCH(k_trace<0>, g.trace_blocks, 128, stream, sc, a);
+        // (volpath scenes of a few primitives keep the one-ray-per-lane kernel for their extension rays; with a real
+        //  hierarchy the queue form wins there as it does for the path integrator -- same hits either way)
+        if (vol && s->info.num_bvh_nodes <= 64) LJ_LAUNCH(k_trace<0>, g.trace_blocks, 128, stream, sc, a);
         else launch_trace(s, a, 0, stream);
         LJ_CUDA(cudaEventRecord(e2, stream));
         if (vol) {
