@@ -433,6 +433,14 @@ __global__ void __launch_bounds__(128, MODE >= 2 ? LJ_WALK_MIN_BLOCKS : (MODE ==
 // rays).  Group stacks sit in a per-warp global scratch area addressed [entry][ray] (same cache path as local
 // memory, but reachable from whichever lane processes the ray).  Same results as trace8 / k_trace: the step
 // functions are the same (lj_bvh.h) and the equal-t tie policy makes the winner independent of visiting order.
+#ifndef LJ_Q_PRIMS_PER_PASS
+#define LJ_Q_PRIMS_PER_PASS 2
+#endif
+constexpr int kQPrimsPerPass = LJ_Q_PRIMS_PER_PASS;
+#ifndef LJ_Q_NODES_PER_PASS
+#define LJ_Q_NODES_PER_PASS 1
+#endif
+constexpr int kQNodesPerPass = LJ_Q_NODES_PER_PASS;
 constexpr int kQWarps = 4;
 constexpr int kQRays = 2 * LJ_WARP_WIDTH;
 enum { Q_EMPTY = 0, Q_NODE = 1, Q_PRIM = 2, Q_FIN = 3 };
@@ -598,7 +606,7 @@ __global__ void __launch_bounds__(kQWarps * LJ_WARP_WIDTH, 8) k_trace_q(const LJ
             const int nsel = cf + __popc(second) < W ? cf + __popc(second) : W;
             node_passes += kind == Q_NODE;
             prim_passes += kind == Q_PRIM;
-            bool finished = false;
+            bool finished = false, more = false;
             if (lane < nsel) {
                 // (each kind of step reads and writes only the fields it needs: the kernel is bound by the shared-memory /
                 //  L1 data pipe, profiles/r02b_sponza_ncu.txt)
@@ -637,6 +645,16 @@ __global__ void __launch_bounds__(kQWarps * LJ_WARP_WIDTH, 8) k_trace_q(const LJ
                         node_steps++;
                         trav_node(sc.nodes8, tr, stk, a.one_bits);
                         trav_next_group(tr, stk);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                        for (int extra = 1; extra < kQNodesPerPass; extra++) {  // (a ray that still wants a node step takes it now)
+                            if (tr.Gt.y == 0 && tr.G.y != 0) {
+                                node_steps++; more = true;
+                                trav_node(sc.nodes8, tr, stk, a.one_bits);
+                                trav_next_group(tr, stk);
+                            }
+                        }
                         q.Gx[r] = tr.G.x; q.Gy[r] = tr.G.y; q.Tx[r] = tr.Gt.x; q.Ty[r] = tr.Gt.y;
                         if (tr.sp != sp0) q.sp[r] = (uint32_t)tr.sp;
                         const uint32_t st = q_status_of(tr);
@@ -649,7 +667,16 @@ __global__ void __launch_bounds__(kQWarps * LJ_WARP_WIDTH, 8) k_trace_q(const LJ
                         tr.G.x = 0; tr.G.y = q.Gy[r];  // (G.x is only needed once the group is entered: it stays in the table)
                         tr.Gt.x = q.Tx[r]; tr.Gt.y = q.Ty[r];
                         prim_tests++;
-                        const bool ended = trav_prim<SHADOW>(sc.prims, tr);  // any-hit ends at the first hit
+                        bool ended = trav_prim<SHADOW>(sc.prims, tr);  // any-hit ends at the first hit
+                        // up to kQPrimsPerPass primitives of the ray's group in one pass, in the group's own order (the
+                        // answers cannot change): selecting a ray and moving its state costs about three times what one
+                        // primitive test does, and most groups hold two or three primitives
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                        for (int extra = 1; extra < kQPrimsPerPass; extra++) {
+                            if (!ended && tr.Gt.y != 0) { prim_tests++; more = true; ended = trav_prim<SHADOW>(sc.prims, tr); }
+                        }
                         if (ended) trav_terminate(tr);
                         if (tr.hit.t != t0 || tr.hit.prim != p0) { q.tfar[r] = tr.hit.t; q.prim[r] = tr.hit.prim; }
                         const bool pop = !ended && (tr.G.y | tr.Gt.y) == 0 && tr.sp > 0;
@@ -670,6 +697,7 @@ __global__ void __launch_bounds__(kQWarps * LJ_WARP_WIDTH, 8) k_trace_q(const LJ
             }
             if (kind == Q_FIN) cF -= nsel;
             else cF += __popc(__ballot_sync(0xffffffffu, finished));  // (the ballot also orders the shared-memory writes)
+            if ((kQPrimsPerPass > 1 || kQNodesPerPass > 1) && kind != Q_FIN && __ballot_sync(0xffffffffu, more)) { if (kind == Q_PRIM) prim_passes++; else node_passes++; }  // (statistics: a pass with second tests counts twice)
             __syncwarp();
         }
     }
