@@ -1200,7 +1200,10 @@ struct Tuning {
     int trace_kernel = 1, q_refill = 48, q_chunk = 128;
     int lambert_kernel = 1;  // scenes with Lambertian materials only: k_shade<.., kMatLambert> (0: the general kernel, A/B)
     int walk_kernel = 1;  // volpath NEE walk: 0 = k_trace<2|3> (one lane per walk), 1 = staged kernels for grid media, 2 = staged for every scene
-    int q_blocks = 0, q_carveout = -1;  // resident CTAs of k_trace_q per SM (0: what fits), shared-memory carve-out in % (-1: the maximum)
+    // resident CTAs of k_trace_q per SM (0: what fits); shared-memory carve-out in % (-1: the maximum).  8 CTAs need 8 x 17.9 KB =
+    // 63 % of the SM's 228 KB; asking for just that leaves 64 KB more L1 than the maximum carve-out does: sponza extend stage
+    // 283 -> 264 ms per 256 spp (profiles/r02ze_sweeps.txt)
+    int q_blocks = 0, q_carveout = 66;
     bool host_prof = false;
 };
 static const Tuning &tuning() {
