@@ -138,6 +138,7 @@ LJ_HD V3 volume_block_majorant(const DevVolume &v, V3 o, V3 d, float t, float &t
     }
     if (!(fastest > 0)) { t_exit = LJ_INF; return mk3(0); }
     const float nudge = 1e-3f / fastest;  // lands a thousandth of a voxel beyond the face (the blocks are dilated by a node)
+    float t_in = 0;  // distance from the point to the grid box along the ray (0: the point is inside)
     if (!inside) {
         float t0 = 0, t1 = LJ_INF;
         for (int i = 0; i < 3; i++) {
@@ -149,8 +150,12 @@ LJ_HD V3 volume_block_majorant(const DevVolume &v, V3 o, V3 d, float t, float &t
                 t1 = -1;
             }
         }
-        t_exit = t0 <= t1 ? t + t0 + nudge : LJ_INF;
-        return mk3(0);
+        if (!(t0 <= t1)) { t_exit = LJ_INF; return mk3(0); }  // the ray never enters the box
+        // empty space up to a nudge short of the entry face (the bound 0 must not reach into the grid); from there on
+        // the stretch belongs to the block the ray enters
+        if (t0 > 2 * nudge) { t_exit = t + t0 - nudge; return mk3(0); }
+        t_in = t0;
+        for (int i = 0; i < 3; i++) q[i] = fminf(fmaxf(q[i] + dq[i] * t0, 0.f), hi[i]);
     }
     const float B = (float)v.maj_block;
     int cell[3];
@@ -161,7 +166,7 @@ LJ_HD V3 volume_block_majorant(const DevVolume &v, V3 o, V3 d, float t, float &t
         if (dq[i] > 0) te = fminf(te, (hi_face - q[i]) / dq[i]);
         else if (dq[i] < 0) te = fminf(te, (lo_face - q[i]) / dq[i]);
     }
-    t_exit = t + fmaxf(te, 0.f) + nudge;
+    t_exit = t + t_in + fmaxf(te, 0.f) + nudge;
     // One bound for the three channels (the largest): with per-channel block majorants a channel whose density is low
     // in this block is sampled with few tentative collisions while the other channels' weights keep their full range,
     // and the chromatic estimator's variance grows (measured on hetvol_colored: x1.5 .. x8, profiles/r02n_*); with a
