@@ -226,8 +226,16 @@ def main():
         init_dist()
     key, full_spp, cpu_spp = WORKLOADS[args.workload]
     spp = args.spp or full_spp
-    ljs_path, _ = scene_paths(args.workload)
-    desc = ljs.load(ljs_path)
+    # The scene goes through the product's own front end (lajolla_public_b200/host: XML + mesh / image / volume
+    # loaders, `lajolla --dump-ljs`) from the scene file itself; the reference parser's dump (.ljs) is only the
+    # fallback when the scene file did not travel with the checkout.  Outside the timed region either way.
+    ljs_path, xml_path = scene_paths(args.workload)
+    if os.path.exists(xml_path) and os.path.exists(lj.LAJOLLA_CLI):
+        desc = lj.load_scene_description(xml_path)
+        scene_source = "scene XML parsed by the product front end (lajolla --dump-ljs)"
+    else:
+        desc = ljs.load(ljs_path)
+        scene_source = "reference scene flattened to .ljs"
     scene = lj.Scene(desc, device=local_rank)
     info = scene.info()
     w, h = scene.width, scene.height
@@ -337,7 +345,7 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(key, w, h, full_spp), "spp_per_gpu": (s_end - s_begin) if tile_stride == 0 else total_spp, "image_spp": total_spp,
                        "l2_policy": f"path pool ({agg.get('pool_paths', 0)} slots x {336 if key in VOLPATH else 144} B) streams through HBM every wave, larger than the 126 MB L2",
-                       "scene_source": "reference scene flattened to .ljs", "parallelism": f"{args.split}-split x{world} + NCCL reduce (NCCL_NVLS_ENABLE={os.environ.get('NCCL_NVLS_ENABLE', 'default')})" if world > 1 else "single GPU"},
+                       "scene_source": scene_source, "parallelism": f"{args.split}-split x{world} + NCCL reduce (NCCL_NVLS_ENABLE={os.environ.get('NCCL_NVLS_ENABLE', 'default')})" if world > 1 else "single GPU"},
             "mrays_per_s": (agg["closest"] + agg["shadow"]) * world / (ms_total / 1e3) / 1e6,
             "rays_per_sample": (agg["closest"] + agg["shadow"]) / max(agg["samples"], 1),
             "mean_bounces": agg["bounces"] / max(agg["samples"], 1),
