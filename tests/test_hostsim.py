@@ -125,6 +125,29 @@ def test_render_matches_reference_mean(oracle):
     assert np.allclose((a + b) / 4, img, rtol=1e-4, atol=1e-5)
 
 
+def test_shade_queues_do_not_depend_on_the_pool(oracle):
+    """The second shade passes run over compacted slot queues (Disney vertices of the path integrator, surface vertices
+    with a material of the volpath integrator: pool.class_queue).  A path's samples depend on (pixel, sample) only, so the
+    film must not depend on how the paths fall into pools, waves and queue positions: a small pool (many waves, short
+    queues) and a large one give the same image, and the Disney render agrees with the oracle's mean."""
+    sc, ref = pair(oracle, "disney_bsdf")
+    big = sc.render(spp=1, pool_paths=1 << 19)
+    st = sc.last_stats
+    assert st.samples == sc.width * sc.height and st.shade_launches >= 2
+    small = sc.render(spp=1, pool_paths=1 << 13)
+    assert sc.last_stats.waves > 2 * st.waves
+    assert np.all(np.isfinite(big))
+    assert np.allclose(big, small, rtol=1e-4, atol=1e-5)
+    import flip
+    ref_img, _ = ref.render(spp=1)  # (equal spp: the display transform is concave, a noisier image has a darker mean)
+    m, rm = flip.tonemap(big).mean(axis=(0, 1)), flip.tonemap(ref_img).mean(axis=(0, 1))
+    assert np.allclose(m, rm, rtol=0.03), (m, rm)
+    sv, _ = pair(oracle, "vol_cbox")
+    a = sv.render(spp=1, pool_paths=1 << 18)
+    b = sv.render(spp=1, pool_paths=1 << 12)
+    assert np.all(np.isfinite(a)) and np.allclose(a, b, rtol=1e-4, atol=1e-5)
+
+
 @pytest.mark.parametrize("name", ["volpath_test6", "hetvol", "hetvol_colored"])
 def test_medium_parity(oracle, name):
     sc, ref = pair(oracle, name)
