@@ -17,12 +17,14 @@ import oracle_lib
 pytestmark = pytest.mark.gpu
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
 
-# scene -> (spp of the GPU render, bound on mean FLIP, bound on the relative difference of the mean colour)
+# scene -> (spp of the GPU render, bound on mean FLIP, bound on the relative difference of the mean colour).  The BASELINE
+# configurations render at BASELINE.json's sample counts (cbox 64 would be below the figure's own: 256; veach_mi 256, the
+# Disney array 256, sponza 1024, the volpath scenes 1024).
 CASES = {
-    "cbox": (256, 0.06, 0.03), "veach_mi": (256, 0.06, 0.03), "sponza": (128, 0.08, 0.04), "matpreview": (128, 0.09, 0.04),
+    "cbox": (256, 0.06, 0.03), "veach_mi": (256, 0.06, 0.03), "sponza": (1024, 0.08, 0.04), "matpreview": (128, 0.09, 0.04),
     "pixel_filter_test": (64, 0.06, 0.03), "pixel_filter_box": (64, 0.06, 0.03), "pixel_filter_tent": (64, 0.06, 0.03),
     "disney_diffuse": (128, 0.08, 0.03), "disney_metal": (128, 0.08, 0.03), "disney_clearcoat": (128, 0.08, 0.03),
-    "disney_glass": (128, 0.09, 0.03), "disney_sheen": (128, 0.08, 0.03), "disney_bsdf_array": (128, 0.09, 0.03),
+    "disney_glass": (128, 0.09, 0.03), "disney_sheen": (128, 0.08, 0.03), "disney_bsdf_array": (256, 0.09, 0.03),
     # volpath_test1 (absorption only): the device runs the general estimator, whose sample is Le or 0 (collision =
     # absorption); the handout's version-1 estimator evaluates the transmittance in closed form.  A tone-mapped mean
     # needs the CONVERGED image, hence the sample count.
@@ -33,7 +35,7 @@ CASES = {
     # between this estimator's depth-4 and depth-5 renders, 0.063 / 0.076, and its caption describes a scene with an
     # inner sphere the shipped XML does not have).  Recorded, with a bound that only catches gross errors.
     "volpath_test5_2": (1024, 0.06, 0.10), "volpath_test6": (1024, 0.06, 0.03), "vol_cbox": (1024, 0.10, 0.03),
-    "vol_cbox_teapot": (1024, 0.06, 0.03), "hetvol": (128, 0.06, 0.03), "hetvol_colored": (128, 0.08, 0.03),
+    "vol_cbox_teapot": (1024, 0.06, 0.03), "hetvol": (1024, 0.06, 0.03), "hetvol_colored": (1024, 0.08, 0.03),
 }
 
 
