@@ -240,7 +240,8 @@ typedef struct lj_trace_opts {
     int32_t kernel;      /* LJ_TRACE_* */
     int32_t pool_paths;  /* path-pool slots (0: sized to the batch); batches larger than the pool run in rounds */
     int32_t slot_stride; /* the rays occupy every slot_stride-th slot, the other slots hold no path (<= 1: dense) */
-    int32_t _pad;
+    int32_t walk_rounds; /* LJ_TRACE_WALK_STAGED: rounds of [segment traversal -> tracking] before the remaining walks finish
+                            as whole loops (0: what lj_render uses); tests lower it to exercise that last kernel */
 } lj_trace_opts;
 int lj_trace_closest_ex(lj_scene *scene, const lj_ray *rays, int64_t n, const lj_trace_opts *opts, lj_hit *hits, double *kernel_ms);
 int lj_trace_any_ex(lj_scene *scene, const lj_ray *rays, int64_t n, const lj_trace_opts *opts, uint8_t *occluded, double *kernel_ms);

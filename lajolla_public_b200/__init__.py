@@ -178,12 +178,12 @@ class Scene:
         abi.check(self._lib.lj_medium_bound_batch(self._h, _ptr(q, abi.lj_medium_query), q.shape[0], _ptr(out, abi.lj_medium_bound)))
         return out
 
-    def nee_walks(self, queries, kernel=abi.LJ_TRACE_PLAIN, pool_paths=0, slot_stride=1, want_ms=False):
+    def nee_walks(self, queries, kernel=abi.LJ_TRACE_PLAIN, pool_paths=0, slot_stride=1, want_ms=False, walk_rounds=0):
         """The volpath integrator's NEE walk for a batch of (origin, light point) queries: (n, 3) contributions."""
         q = np.ascontiguousarray(queries, dtype=WALK_QUERY_DTYPE)
         out = np.zeros((q.shape[0], 3), dtype=np.float32)
         ms = C.c_double(0)
-        opts = abi.lj_trace_opts(kernel, pool_paths, slot_stride, 0)
+        opts = abi.lj_trace_opts(kernel, pool_paths, slot_stride, walk_rounds)
         abi.check(self._lib.lj_nee_walk_batch(self._h, _ptr(q, abi.lj_walk_query), q.shape[0], C.byref(opts), _ptr(out, C.c_float), C.byref(ms)))
         return (out, ms.value) if want_ms else out
 

@@ -90,7 +90,7 @@ class lj_ray(C.Structure):
 
 
 class lj_trace_opts(C.Structure):
-    _fields_ = [("kernel", i32), ("pool_paths", i32), ("slot_stride", i32), ("_pad", i32)]
+    _fields_ = [("kernel", i32), ("pool_paths", i32), ("slot_stride", i32), ("walk_rounds", i32)]
 
 
 LJ_TRACE_PLAIN, LJ_TRACE_WAVEFRONT, LJ_TRACE_WAVEFRONT_LANE, LJ_TRACE_WALK_WHOLE, LJ_TRACE_WALK_STEP, LJ_TRACE_WALK_STAGED = 0, 1, 2, 3, 4, 5

@@ -1323,20 +1323,20 @@ static void launch_trace(lj_scene *s, const WaveArgs &a, int mode, cudaStream_t 
 static bool walk_staged(const lj_scene *s) {
     return tuning().walk_kernel == 2 || (tuning().walk_kernel == 1 && (s->has_grid_media || s->info.num_bvh_nodes > 64));
 }
-static uint64_t launch_walk_staged(lj_scene *s, const WaveArgs &a, cudaStream_t stream) {
+static uint64_t launch_walk_staged(lj_scene *s, const WaveArgs &a, cudaStream_t stream, int rounds = kWalkRounds) {
     const DevScene &sc = s->dev;
     const int nb256 = (a.pool.capacity + 255) / 256, nb128 = (a.pool.capacity + 127) / 128;
     LJ_LAUNCH(k_walk_begin, nb256, 256, stream, sc, a);
     WaveArgs v = a;  // the walk view of the pool: the pending segments are the "rays", w_meta says which slots hold one
     v.pool.ray_o = a.pool.w_o; v.pool.ray_d = a.pool.w_d; v.pool.hit = a.pool.w_hit; v.pool.meta = a.pool.w_meta;
     v.closest_counter = C_SHADOW;
-    for (int r = 0; r < kWalkRounds; r++) {
+    for (int r = 0; r < rounds; r++) {
         cudaMemsetAsync(s->d_cursors, 0, 2 * sizeof(unsigned int), stream);
         LJ_LAUNCH(k_trace_q<0>, s->geom.q_blocks, kQWarps * LJ_WARP_WIDTH, stream, sc, v);
         LJ_LAUNCH(k_walk_track, s->geom.wtrack_blocks, 128, stream, sc, a);
     }
     LJ_LAUNCH(k_walk_finish, nb128, 128, stream, sc, a);
-    return 2 + 2 * kWalkRounds;
+    return 2 + 2 * (uint64_t)rounds;
 }
 
 static int ensure_render_buffers(lj_scene *s, int npix, bool want_sq) {
@@ -1766,7 +1766,7 @@ static int walk_batch_impl(lj_scene *s, const lj_walk_query *q, int64_t n, const
             cudaMemsetAsync(s->d_cursors, 0, 4 * sizeof(unsigned int), stream);
             cudaMemsetAsync(s->d_counters, 0, sizeof(unsigned long long) * C_TOTAL, stream);
             cudaEventRecord(s->ev[0], stream);
-            if (kernel == LJ_TRACE_WALK_STAGED) launch_walk_staged(s, a, stream);
+            if (kernel == LJ_TRACE_WALK_STAGED) launch_walk_staged(s, a, stream, opts->walk_rounds > 0 ? std::min(opts->walk_rounds, 64) : kWalkRounds);
             else if (kernel == LJ_TRACE_WALK_STEP) LJ_LAUNCH(k_trace<3>, s->geom.step_blocks, 128, stream, s->dev, a);
             else LJ_LAUNCH(k_trace<2>, s->geom.walk_blocks, 128, stream, s->dev, a);
             cudaEventRecord(s->ev[1], stream);

@@ -131,10 +131,12 @@ def check_walk_parity(scene, ref, n, configs):
     q = make_walk_queries(scene, ref, n)
     base = scene.nee_walks(q)
     assert np.all(np.isfinite(base))
-    for kernel, pool, stride in configs:
-        got = scene.nee_walks(q, kernel=kernel, pool_paths=pool, slot_stride=stride)
+    for cfg in configs:  # (kernel, pool_paths, slot_stride[, rounds of the staged walk before its whole-loop finish kernel])
+        kernel, pool, stride = cfg[:3]
+        rounds = cfg[3] if len(cfg) > 3 else 0
+        got = scene.nee_walks(q, kernel=kernel, pool_paths=pool, slot_stride=stride, walk_rounds=rounds)
         bad = got.view(np.uint32) != base.view(np.uint32)
-        assert not bad.any(), f"walk kernel {kernel} pool {pool} stride {stride}: {int(bad.any(axis=1).sum())} of {n} walks differ, e.g. {got[bad.any(axis=1)][:2]} vs {base[bad.any(axis=1)][:2]}"
+        assert not bad.any(), f"walk kernel {kernel} pool {pool} stride {stride} rounds {rounds}: {int(bad.any(axis=1).sum())} of {n} walks differ, e.g. {got[bad.any(axis=1)][:2]} vs {base[bad.any(axis=1)][:2]}"
     return dict(n=int(n), unblocked=float((np.abs(base).max(axis=1) > 0).mean()), mean=float(base.mean()), configs=len(configs))
 
 

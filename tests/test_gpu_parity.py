@@ -101,7 +101,8 @@ def test_walk_kernels_parity(oracle, name):
     from lajolla_public_b200 import abi
     sc, ref = pair(oracle, name)
     W, S, G = abi.LJ_TRACE_WALK_WHOLE, abi.LJ_TRACE_WALK_STEP, abi.LJ_TRACE_WALK_STAGED
-    cfg = [(W, 0, 1), (W, 0, 7), (W, 20000, 1), (S, 0, 1), (S, 0, 37), (S, 30000, 3), (S, 1000, 1), (G, 0, 1), (G, 0, 37), (G, 30000, 3), (G, 1000, 1)]
+    cfg = [(W, 0, 1), (W, 0, 7), (W, 20000, 1), (S, 0, 1), (S, 0, 37), (S, 30000, 3), (S, 1000, 1), (G, 0, 1), (G, 0, 37), (G, 30000, 3), (G, 1000, 1),
+           (G, 0, 1, 1), (G, 30000, 3, 2)]  # (one / two rounds: most multi-segment walks end in k_walk_finish)
     record("walk_parity", dict(scene=name, **pc.check_walk_parity(sc, ref, 1 << 16, cfg)))
 
 

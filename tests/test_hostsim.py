@@ -71,7 +71,7 @@ def test_walk_kernels_parity(oracle, name):
     from lajolla_public_b200 import abi
     sc, ref = pair(oracle, name)
     W, S, G = abi.LJ_TRACE_WALK_WHOLE, abi.LJ_TRACE_WALK_STEP, abi.LJ_TRACE_WALK_STAGED
-    r = pc.check_walk_parity(sc, ref, 600 if name == "hetvol" else 2000, [(W, 0, 1), (S, 0, 1), (S, 1000, 3), (G, 0, 1), (G, 1000, 3)])
+    r = pc.check_walk_parity(sc, ref, 600 if name == "hetvol" else 2000, [(W, 0, 1), (S, 0, 1), (S, 1000, 3), (G, 0, 1), (G, 1000, 3), (G, 0, 1, 1), (G, 1000, 3, 2)])
     assert r["unblocked"] > 0.05
 
 
