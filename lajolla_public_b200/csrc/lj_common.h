@@ -15,7 +15,7 @@
 // One copy per translation unit instead of one per call site: the material dispatchers are called five times per
 // shade and inlining them made k_shade 1.5 MB of SASS, which the instruction caches cannot hold when the warps of an
 // SM sit in different materials (disney_bsdf: 8 % of issue slots used, the rest waiting for instructions).
-#define LJ_HD_CALL static __host__ __device__ __noinline__
+#define LJ_HD_CALL __attribute__((unused)) static __host__ __device__ __noinline__
 #else
 #define LJ_HD inline
 #define LJ_D inline
